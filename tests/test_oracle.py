@@ -1,0 +1,127 @@
+"""Pins the CPU oracle (oracle/nl_oracle.c) against fixtures produced by the reference's own code
+(tests/golden/make_golden.py): reference quantizer bytes decoded by gguf-py, and logits / greedy streams of the
+reference torch model.  CPU only."""
+import os
+
+import numpy as np
+import pytest
+
+from nanollama_b200 import gguf as G
+from oracle import oracle as O
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "dequant_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden_logits.npz"))
+
+
+def test_half2float_all_65536(kat):
+    # go/gguf.go:601-636 LUT == IEEE binary16->binary32 for every bit pattern (NaN payloads included)
+    # (through memory, not a float return register, so signalling-NaN payloads are not quieted on the way)
+    allh = np.arange(65536, dtype=np.uint16)
+    got = O.dequant(G.GGML_F16, allh.view(np.uint8), 65536).view(np.uint32)
+    assert np.array_equal(got, kat["half_all_expect"])
+
+
+@pytest.mark.parametrize("key,typ", [("q4_0", G.GGML_Q4_0), ("q8_0", G.GGML_Q8_0), ("q8_0_requant", G.GGML_Q8_0), ("f16", G.GGML_F16)])
+def test_dequant_bit_exact_vs_reference_bytes(kat, key, typ):
+    raw = kat[key + "_bytes"]
+    got = O.dequant(typ, raw, 2048).view(np.uint32)
+    assert np.array_equal(got, kat[key + "_expect"])
+
+
+def test_matmul_equals_dequant_then_dot_ordering(kat):
+    # MatMulQ4_0 applies the scale after the per-block dot (go/quant.go:83-90); check against an explicit restatement
+    rng = np.random.default_rng(0)
+    rows, cols = 8, 256
+    w = rng.standard_normal((rows, cols)).astype(np.float32)
+    x = rng.standard_normal(cols).astype(np.float32)
+    for typ, q in ((G.GGML_Q4_0, G.quantize_q4_0(w)), (G.GGML_Q8_0, G.quantize_q8_0(w))):
+        got = O.matmul(q, typ, x, rows, cols)
+        bs = G.ggml_block_size(typ)
+        blocks = q.reshape(rows, cols // 32, bs)
+        exp = np.zeros(rows, dtype=np.float32)
+        for r in range(rows):
+            s = np.float32(0)
+            for b in range(cols // 32):
+                d = blocks[r, b, :2].view(np.float16).astype(np.float32)[0]
+                dot = np.float32(0)
+                if typ == G.GGML_Q4_0:
+                    for j in range(16):
+                        bv = int(blocks[r, b, 2 + j])
+                        v0 = np.float32((bv & 15) - 8)
+                        v1 = np.float32((bv >> 4) - 8)
+                        dot = np.float32(dot + np.float32(np.float32(v0 * x[b * 32 + j]) + np.float32(v1 * x[b * 32 + j + 16])))
+                else:
+                    for j in range(32):
+                        dot = np.float32(dot + np.float32(np.float32(np.int8(blocks[r, b, 2 + j])) * x[b * 32 + j]))
+                s = np.float32(s + np.float32(dot * d))
+            exp[r] = s
+        assert np.array_equal(got.view(np.uint32), exp.view(np.uint32))
+
+
+def test_matmul_threading_invariant():
+    rng = np.random.default_rng(1)
+    rows, cols = 512, 128
+    q = G.quantize_q8_0(rng.standard_normal((rows, cols)).astype(np.float32))
+    x = rng.standard_normal(cols).astype(np.float32)
+    O.set_workers(1)
+    a = O.matmul(q, G.GGML_Q8_0, x, rows, cols)
+    O.set_workers(7)
+    b = O.matmul(q, G.GGML_Q8_0, x, rows, cols)
+    O.set_workers(os.cpu_count() or 1)
+    assert np.array_equal(a.view(np.uint32), b.view(np.uint32))
+
+
+def test_unsupported_type_rejected():
+    with pytest.raises(ValueError):
+        O.dequant(3, np.zeros(20, np.uint8), 32)  # Q4_1: parsed by gguf.go but no Dequant/MatMul exists
+
+
+FILES = ["tiny_gqa_f16", "tiny_gqa_q8_0", "tiny_gqa_q8_0_requant", "tiny_gqa_q4_0", "tiny_mha_qknorm_q8_0"]
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_forward_logits_vs_reference_torch_model(golden_dir, gold, name):
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m = O.OracleModel(gf)
+    toks = gold["tokens"]
+    exp = gold[name + "_logits"]
+    m.reset()
+    worst = 0.0
+    for pos, t in enumerate(toks):
+        lg = m.forward(int(t), pos)
+        # BASELINE.json tolerance is 1e-3 max-rel; the two fp32 implementations agree far tighter
+        err = np.abs(lg - exp[pos]).max() / np.abs(exp[pos]).max()
+        worst = max(worst, float(err))
+        assert int(np.argmax(lg)) == int(np.argmax(exp[pos]))
+    assert worst < 2e-5, worst
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_greedy_stream_vs_reference_torch_model(golden_dir, gold, name):
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m = O.OracleModel(gf)
+    exp = gold[name + "_greedy"]
+    got, margins = m.generate_greedy(gold["tokens"][:8], len(exp))
+    # identical wherever the top-1/top-2 margin is not at fp32-noise level
+    n = len(exp)
+    bad = [i for i in range(min(n, len(got))) if got[i] != exp[i]]
+    if bad:
+        assert margins[bad[0]] < 1e-4, (bad[0], margins[bad[0]])
+    else:
+        assert len(got) == n
+
+
+def test_forward_rejects_out_of_range(golden_dir):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = O.OracleModel(gf)
+    with pytest.raises(IndexError):
+        m.forward(256, 0)
+    with pytest.raises(IndexError):
+        m.forward(1, 64)
