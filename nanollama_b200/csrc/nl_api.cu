@@ -1,0 +1,731 @@
+// nl_api.cu — model object, per-token launch sequence (CUDA graph) and the C ABI of libnanollama_cuda.so.
+// Replaces LoadLlamaModel / Forward / Reset (go/model.go:121-631) and the greedy loop of Engine.Generate (go/main.go:152-230).
+#include <math.h>
+#include <stdarg.h>
+#include <stdio.h>
+#include <string.h>
+
+#include <vector>
+
+#include "nl_gemv.cuh"
+#include "nl_kernels.cuh"
+
+namespace nl {
+
+static thread_local char g_err[512] = "";
+void set_error(const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+}
+int fail(int code, const char *fmt, ...) {
+    va_list ap; va_start(ap, fmt); vsnprintf(g_err, sizeof g_err, fmt, ap); va_end(ap);
+    return code;
+}
+
+static bool type_planar(int t) { return t == NL_Q4_0 || t == NL_Q8_0; }
+static bool type_supported(int t) { return blk_bytes(t) != 0; }
+
+static void free_mat(DevMat &m) {
+    if (m.qs) cudaFree(m.qs);
+    if (m.d) cudaFree(m.d);
+    m = DevMat();
+}
+
+// Upload a [rows, cols] tensor from host GGUF bytes into the planar device layout.
+static int upload_mat(DevMat &m, int type, int64_t rows, int64_t cols, const void *host, size_t nbytes, cudaStream_t st) {
+    if (!type_supported(type)) return fail(NL_ERR_UNSUPPORTED, "unsupported tensor type %d", type);
+    if (rows <= 0 || cols <= 0 || cols % blk_elems(type) != 0) return fail(NL_ERR_INVALID, "bad shape %lldx%lld for type %d", (long long)rows, (long long)cols, type);
+    if ((type == NL_F16 && cols % 8) || (type == NL_F32 && cols % 4)) return fail(NL_ERR_INVALID, "cols %lld not a multiple of the 16-byte unit", (long long)cols);
+    int64_t expect = tensor_nbytes(type, rows * cols);
+    if ((int64_t)nbytes != expect) return fail(NL_ERR_INVALID, "tensor has %zu bytes, expected %lld", nbytes, (long long)expect);
+    free_mat(m);
+    m.type = type; m.rows = rows; m.cols = cols;
+    if (type_planar(type)) {
+        int64_t nblocks = rows * cols / 32;
+        m.qs_bytes = (size_t)nblocks * (type == NL_Q4_0 ? 16 : 32);
+        m.d_bytes = (size_t)nblocks * 2;
+        uint8_t *staging = nullptr;
+        NL_CUDA(cudaMalloc(&staging, nbytes));
+        cudaError_t e = cudaMalloc(&m.qs, m.qs_bytes);
+        if (e == cudaSuccess) e = cudaMalloc(&m.d, m.d_bytes);
+        if (e != cudaSuccess) { cudaFree(staging); free_mat(m); return fail(NL_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+        e = cudaMemcpyAsync(staging, host, nbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) {
+            int threads = 256; int64_t grid = (nblocks + threads - 1) / threads;
+            if (type == NL_Q4_0) repack_q4_0_kernel<<<(unsigned)grid, threads, 0, st>>>(staging, (uint4 *)m.qs, m.d, nblocks);
+            else repack_q8_0_kernel<<<(unsigned)grid, threads, 0, st>>>(staging, (uint4 *)m.qs, m.d, nblocks);
+            e = cudaGetLastError();
+        }
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        cudaFree(staging);
+        if (e != cudaSuccess) { free_mat(m); return fail(NL_ERR_CUDA, "upload/repack: %s", cudaGetErrorString(e)); }
+    } else {
+        m.qs_bytes = nbytes;
+        cudaError_t e = cudaMalloc(&m.qs, nbytes);
+        if (e != cudaSuccess) { free_mat(m); return fail(NL_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+        e = cudaMemcpyAsync(m.qs, host, nbytes, cudaMemcpyHostToDevice, st);
+        if (e == cudaSuccess) e = cudaStreamSynchronize(st);
+        if (e != cudaSuccess) { free_mat(m); return fail(NL_ERR_CUDA, "upload: %s", cudaGetErrorString(e)); }
+    }
+    return NL_OK;
+}
+
+// planar/raw device matrix -> fp32 (n = rows*cols elements)
+static int dequant_mat(const DevMat &m, float *out, cudaStream_t st) {
+    int64_t n = m.rows * m.cols;
+    int threads = 256;
+    if (m.type == NL_Q4_0) dequant_q4_0_kernel<<<(unsigned)((n / 32 + threads - 1) / threads), threads, 0, st>>>((const uint4 *)m.qs, m.d, out, n / 32);
+    else if (m.type == NL_Q8_0) dequant_q8_0_kernel<<<(unsigned)((n / 32 + threads - 1) / threads), threads, 0, st>>>((const uint4 *)m.qs, m.d, out, n / 32);
+    else if (m.type == NL_F16) dequant_f16_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>((const __half *)m.qs, out, n);
+    else if (m.type == NL_F32) NL_CUDA(cudaMemcpyAsync(out, m.qs, n * 4, cudaMemcpyDeviceToDevice, st));
+    else dequant_raw_kernel<<<(unsigned)((n + threads - 1) / threads), threads, 0, st>>>(m.type, m.qs, out, n);
+    NL_CUDA(cudaGetLastError());
+    return NL_OK;
+}
+
+// ---- GEMV dispatch on (type, batch) ----
+struct MatRef { const DevMat *w; const DevMat *w2; const float *bias; float *out; int out_stride; };
+
+static int gemv_multi(const MatRef *mats, int nmat, const float *x, int x_stride, int batch, int epi, cudaStream_t st) {
+    const DevMat &w0 = *mats[0].w;
+    const int type = w0.type;
+    for (int b0 = 0; b0 < batch;) {
+        int nb = (batch - b0 >= 4) ? 4 : (batch - b0 >= 2 ? 2 : 1);
+        if (type == NL_Q4_0 || type == NL_Q8_0 || type == NL_F16 || type == NL_F32) {
+            GemvArgs a; memset(&a, 0, sizeof a);
+            a.nseg = nmat; a.x = x + (int64_t)b0 * x_stride; a.x_stride = x_stride; a.cols = (int)w0.cols;
+            for (int i = 0; i < nmat; i++) {
+                const DevMat &w = *mats[i].w;
+                if (w.type != type || w.cols != w0.cols) return fail(NL_ERR_INVALID, "fused GEMV segments differ in type/cols");
+                a.seg[i].qs = w.qs; a.seg[i].d = w.d;
+                if (epi == EPI_SWIGLU) { a.seg[i].qs2 = mats[i].w2->qs; a.seg[i].d2 = mats[i].w2->d; }
+                a.seg[i].bias = mats[i].bias; a.seg[i].out = mats[i].out + (int64_t)b0 * mats[i].out_stride;
+                a.seg[i].rows = (int)w.rows; a.seg[i].out_stride = mats[i].out_stride;
+            }
+            int rc = type == NL_Q4_0 ? launch_gemv_q4_0(a, nb, epi, st) : type == NL_Q8_0 ? launch_gemv_q8_0(a, nb, epi, st)
+                   : type == NL_F16 ? launch_gemv_f16(a, nb, epi, st) : launch_gemv_f32(a, nb, epi, st);
+            if (rc) return fail(NL_ERR_INVALID, "gemv launch: bad batch %d", nb);
+        } else {
+            if (epi == EPI_SWIGLU) return fail(NL_ERR_STATE, "internal: swiglu epilogue on raw-block type");
+            for (int i = 0; i < nmat; i++) {
+                const DevMat &w = *mats[i].w;
+                int warps = 8; unsigned grid = (unsigned)((w.rows + warps - 1) / warps);
+                const float *xx = x + (int64_t)b0 * x_stride; float *oo = mats[i].out + (int64_t)b0 * mats[i].out_stride;
+                if (nb == 4) gemv_raw_kernel<4><<<grid, warps * 32, 0, st>>>(w.type, w.qs, xx, x_stride, oo, mats[i].out_stride, mats[i].bias, (int)w.rows, (int)w.cols, epi);
+                else if (nb == 2) gemv_raw_kernel<2><<<grid, warps * 32, 0, st>>>(w.type, w.qs, xx, x_stride, oo, mats[i].out_stride, mats[i].bias, (int)w.rows, (int)w.cols, epi);
+                else gemv_raw_kernel<1><<<grid, warps * 32, 0, st>>>(w.type, w.qs, xx, x_stride, oo, mats[i].out_stride, mats[i].bias, (int)w.rows, (int)w.cols, epi);
+            }
+        }
+        b0 += nb;
+    }
+    NL_CUDA(cudaGetLastError());
+    return NL_OK;
+}
+
+__global__ void swiglu_kernel(float *__restrict__ hb, const float *__restrict__ hb2, int64_t n) {
+    int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
+    if (i < n) hb[i] = silu_f(hb[i]) * hb2[i];
+}
+
+}  // namespace nl
+
+using namespace nl;
+
+// =====================================================================================================
+struct Layer {
+    float *attn_norm = nullptr, *ffn_norm = nullptr, *bq = nullptr, *bk = nullptr, *bv = nullptr, *bo = nullptr;
+    DevMat wq, wk, wv, wo, wgate, wup, wdown;
+};
+
+struct nl_model {
+    nl_config c;
+    int dim = 0, hd = 0, kvd = 0, qdim = 0, B = 1;
+    cudaStream_t st = nullptr;
+    DevMat tok_embd, output;
+    float *output_norm = nullptr;
+    std::vector<Layer> L;
+    float *gamma = nullptr; int32_t *gamma_map = nullptr;
+    // state (all [B][...])
+    float *x = nullptr, *xb = nullptr, *xb2 = nullptr, *hb = nullptr, *hb2 = nullptr, *q = nullptr, *k = nullptr, *v = nullptr, *logits = nullptr;
+    float *kc = nullptr, *vc = nullptr;  // [B][L][S][kvd]
+    float *cos_t = nullptr, *sin_t = nullptr;
+    int32_t *d_token = nullptr, *d_pos = nullptr, *d_gen = nullptr, *d_gen_count = nullptr, *d_prompt = nullptr, *d_cursor = nullptr;
+    int gen_cap = 0, prompt_cap = 0;
+    int32_t *h_stage = nullptr;  // pinned: tokens[B], pos[B]
+    float *h_logits = nullptr;   // pinned [B][vocab]
+    bool finalized = false;
+    std::vector<cudaGraphExec_t> g_fwd, g_step;  // index = batch
+    int launches_fwd = 0;
+    int64_t weight_bytes = 0;
+    cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+};
+
+static int set_dev(const nl_model *m) {
+    NL_CUDA(cudaSetDevice(m->c.device));
+    return NL_OK;
+}
+
+static int upload_vec(float **dst, int type, int64_t n, const void *host, size_t nbytes, cudaStream_t st) {
+    DevMat tmp;
+    int rc = upload_mat(tmp, type, 1, n, host, nbytes, st);
+    if (rc) return rc;
+    if (*dst) cudaFree(*dst);
+    *dst = nullptr;
+    cudaError_t e = cudaMalloc(dst, n * 4);
+    if (e != cudaSuccess) { free_mat(tmp); return fail(NL_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    rc = dequant_mat(tmp, *dst, st);  // getF32Tensor, go/model.go:268-303
+    if (rc == NL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(NL_ERR_CUDA, "dequant vector failed");
+    free_mat(tmp);
+    return rc;
+}
+
+// The launch sequence of one Forward for `batch` sequences (go/model.go:490-620).  Recorded into a CUDA graph.
+static int record_forward(nl_model *m, int batch) {
+    const nl_config &c = m->c;
+    cudaStream_t st = m->st;
+    const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = c.interm_size;
+    int launches = 0;
+    {   // 1. embedding (+gamma), model.go:500-507
+        dim3 grid((dim + 255) / 256, batch);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim);
+        launches++;
+    }
+    const int nthreads_norm = dim >= 4096 ? 1024 : dim >= 1024 ? 512 : 256;
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, ly.attn_norm, m->xb, dim, c.rms_norm_eps); launches++;
+        {   // Q, K, V projections (+bias), model.go:520-527 — one launch when the three share a type
+            MatRef r[3] = {{&ly.wq, nullptr, ly.bq, m->q, qdim}, {&ly.wk, nullptr, ly.bk, m->k, kvd}, {&ly.wv, nullptr, ly.bv, m->v, kvd}};
+            if (ly.wq.type == ly.wk.type && ly.wq.type == ly.wv.type && type_supported(ly.wq.type) && blk_elems(ly.wq.type) <= 32) {
+                int rc = gemv_multi(r, 3, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++;
+            } else {
+                for (int i = 0; i < 3; i++) { int rc = gemv_multi(&r[i], 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++; }
+            }
+        }
+        {   // RoPE, QK-norm, KV write, attention: model.go:530-587
+            AttnArgs a;
+            a.q = m->q; a.k = m->k; a.v = m->v;
+            a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
+            a.seq_stride = (int64_t)c.n_layers * S * kvd;
+            a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.pos = m->d_pos; a.out = m->xb2;
+            a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads; a.seq_len = S; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate;
+            a.eps = c.rms_norm_eps; a.scale = (float)(1.0 / sqrt((double)hd));
+            dim3 grid(c.n_heads, batch);
+            if (hd == 64) attn_decode_kernel<64><<<grid, 128, S * sizeof(float), st>>>(a);
+            else attn_decode_kernel<128><<<grid, 128, S * sizeof(float), st>>>(a);
+            launches++;
+        }
+        {   // output projection + residual, model.go:590-594
+            MatRef r = {&ly.wo, nullptr, ly.bo, m->x, dim};
+            int rc = gemv_multi(&r, 1, m->xb2, qdim, batch, EPI_RESID, st); if (rc) return rc; launches++;
+        }
+        rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, ly.ffn_norm, m->xb, dim, c.rms_norm_eps); launches++;
+        {   // gate/up + SiLU*up, model.go:600-606
+            bool fused = ly.wgate.type == ly.wup.type && (ly.wgate.type == NL_Q4_0 || ly.wgate.type == NL_Q8_0 || ly.wgate.type == NL_F16 || ly.wgate.type == NL_F32);
+            if (fused) {
+                MatRef r = {&ly.wgate, &ly.wup, nullptr, m->hb, ffn};
+                int rc = gemv_multi(&r, 1, m->xb, dim, batch, EPI_SWIGLU, st); if (rc) return rc; launches++;
+            } else {
+                MatRef g = {&ly.wgate, nullptr, nullptr, m->hb, ffn}, u = {&ly.wup, nullptr, nullptr, m->hb2, ffn};
+                int rc = gemv_multi(&g, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc;
+                rc = gemv_multi(&u, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc;
+                int64_t n = (int64_t)batch * ffn;
+                swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->hb, m->hb2, n);
+                launches += 3;
+            }
+        }
+        {   // down projection + residual, model.go:609-612
+            MatRef r = {&ly.wdown, nullptr, nullptr, m->x, dim};
+            int rc = gemv_multi(&r, 1, m->hb, ffn, batch, EPI_RESID, st); if (rc) return rc; launches++;
+        }
+    }
+    rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, m->output_norm, m->xb, dim, c.rms_norm_eps); launches++;  // model.go:616
+    {   // LM head, model.go:619
+        const DevMat &out = m->output.present() ? m->output : m->tok_embd;
+        MatRef r = {&out, nullptr, nullptr, m->logits, c.vocab_size};
+        int rc = gemv_multi(&r, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++;
+    }
+    NL_CUDA(cudaGetLastError());
+    m->launches_fwd = launches;
+    return NL_OK;
+}
+
+static int record_advance(nl_model *m, int batch) {
+    StepState s{m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->gen_cap};
+    argmax_advance_kernel<<<batch, 1024, 0, m->st>>>(m->logits, m->c.vocab_size, s);
+    NL_CUDA(cudaGetLastError());
+    return NL_OK;
+}
+
+static int build_graphs(nl_model *m, int batch) {
+    if ((int)m->g_fwd.size() <= batch) { m->g_fwd.resize(batch + 1, nullptr); m->g_step.resize(batch + 1, nullptr); }
+    if (m->g_fwd[batch]) return NL_OK;
+    cudaGraph_t g;
+    NL_CUDA(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
+    int rc = record_forward(m, batch);
+    cudaError_t e = cudaStreamEndCapture(m->st, &g);
+    if (rc) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+    NL_CUDA(e);
+    NL_CUDA(cudaGraphInstantiate(&m->g_fwd[batch], g, 0));
+    cudaGraphDestroy(g);
+    // greedy step: argmax/advance, then forward (go/main.go:173-218)
+    NL_CUDA(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
+    rc = record_advance(m, batch);
+    if (!rc) rc = record_forward(m, batch);
+    e = cudaStreamEndCapture(m->st, &g);
+    if (rc) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+    NL_CUDA(e);
+    NL_CUDA(cudaGraphInstantiate(&m->g_step[batch], g, 0));
+    cudaGraphDestroy(g);
+    return NL_OK;
+}
+
+// =====================================================================================================
+extern "C" {
+
+const char *nl_last_error(void) { return g_err; }
+int nl_abi_version(void) { return NL_ABI_VERSION; }
+
+int nl_device_count(void) {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) { cudaGetLastError(); return 0; }
+    int ok = 0;
+    for (int i = 0; i < n; i++) {
+        int major = 0;
+        if (cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, i) == cudaSuccess && major == 10) ok++;
+    }
+    return ok;
+}
+
+static int check_device(int dev) {
+    int n = 0;
+    cudaError_t e = cudaGetDeviceCount(&n);
+    if (e != cudaSuccess || n == 0) { cudaGetLastError(); return fail(NL_ERR_CUDA, "no CUDA device available (%s); libnanollama_cuda has no CPU fallback", e == cudaSuccess ? "count=0" : cudaGetErrorString(e)); }
+    if (dev < 0 || dev >= n) return fail(NL_ERR_INVALID, "device %d out of range (have %d)", dev, n);
+    int major = 0;
+    NL_CUDA(cudaDeviceGetAttribute(&major, cudaDevAttrComputeCapabilityMajor, dev));
+    if (major != 10) return fail(NL_ERR_CUDA, "device %d has compute capability %d.x; this library is built for sm_100a only", dev, major);
+    NL_CUDA(cudaSetDevice(dev));
+    return NL_OK;
+}
+
+int nl_create(const nl_config *cfg, nl_model **out) {
+    if (!cfg || !out) return fail(NL_ERR_INVALID, "null argument");
+    *out = nullptr;
+    nl_config c = *cfg;
+    if (c.head_dim == 0 && c.n_heads > 0) c.head_dim = c.embed_dim / c.n_heads;  // go/model.go:140-142
+    if (c.seq_len > 2048) c.seq_len = 2048;                                        // go/model.go:145-148
+    if (c.n_kv_heads == 0) c.n_kv_heads = c.n_heads;                               // go/gguf.go:456-458
+    if (c.max_batch <= 0) c.max_batch = 1;
+    if (c.tp_size <= 0) c.tp_size = 1;
+    if (c.n_layers <= 0 || c.embed_dim <= 0 || c.n_heads <= 0 || c.n_kv_heads <= 0 || c.vocab_size <= 0 || c.seq_len <= 0 || c.interm_size <= 0)
+        return fail(NL_ERR_INVALID, "config has a non-positive dimension (layers=%d dim=%d heads=%d kv=%d vocab=%d seq=%d ffn=%d)",
+                    c.n_layers, c.embed_dim, c.n_heads, c.n_kv_heads, c.vocab_size, c.seq_len, c.interm_size);
+    if (c.n_heads % c.n_kv_heads) return fail(NL_ERR_INVALID, "n_heads %d not a multiple of n_kv_heads %d", c.n_heads, c.n_kv_heads);
+    if (c.head_dim != 64 && c.head_dim != 128) return fail(NL_ERR_UNSUPPORTED, "head_dim %d (supported: 64, 128)", c.head_dim);
+    if (c.embed_dim % 32 || c.interm_size % 32) return fail(NL_ERR_INVALID, "embed_dim/interm_size must be multiples of 32");
+    if (c.tp_size != 1) return fail(NL_ERR_UNSUPPORTED, "tp_size %d: tensor parallelism is not built yet", c.tp_size);
+    if (c.max_batch > 64) return fail(NL_ERR_INVALID, "max_batch %d > 64", c.max_batch);
+    int rc = check_device(c.device);
+    if (rc) return rc;
+    nl_model *m = new nl_model();
+    m->c = c; m->dim = c.embed_dim; m->hd = c.head_dim; m->kvd = c.n_kv_heads * c.head_dim; m->qdim = c.n_heads * c.head_dim; m->B = c.max_batch;
+    m->L.resize(c.n_layers);
+    cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
+    if (e != cudaSuccess) { delete m; return fail(NL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
+    *out = m;
+    return NL_OK;
+}
+
+int nl_get_config(const nl_model *m, nl_config *out) {
+    if (!m || !out) return fail(NL_ERR_INVALID, "null argument");
+    *out = m->c;
+    return NL_OK;
+}
+
+int nl_upload_tensor(nl_model *m, int slot, int layer, uint32_t type, int64_t rows, int64_t cols, const void *host, size_t nbytes) {
+    if (!m || !host) return fail(NL_ERR_INVALID, "null argument");
+    if (m->finalized) return fail(NL_ERR_STATE, "upload after nl_finalize");
+    int rc = set_dev(m); if (rc) return rc;
+    const nl_config &c = m->c;
+    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size;
+    if (slot >= NL_ATTN_NORM && (layer < 0 || layer >= c.n_layers)) return fail(NL_ERR_INVALID, "layer %d out of range", layer);
+    Layer *ly = slot >= NL_ATTN_NORM ? &m->L[layer] : nullptr;
+    DevMat *mat = nullptr; float **vec = nullptr; int64_t er = 1, ec = 0;
+    switch (slot) {
+    case NL_TOK_EMBD: mat = &m->tok_embd; er = c.vocab_size; ec = dim; break;
+    case NL_OUTPUT: mat = &m->output; er = c.vocab_size; ec = dim; break;
+    case NL_OUTPUT_NORM: vec = &m->output_norm; ec = dim; break;
+    case NL_ATTN_NORM: vec = &ly->attn_norm; ec = dim; break;
+    case NL_FFN_NORM: vec = &ly->ffn_norm; ec = dim; break;
+    case NL_WQ: mat = &ly->wq; er = qdim; ec = dim; break;
+    case NL_WK: mat = &ly->wk; er = kvd; ec = dim; break;
+    case NL_WV: mat = &ly->wv; er = kvd; ec = dim; break;
+    case NL_WO: mat = &ly->wo; er = dim; ec = qdim; break;
+    case NL_WGATE: mat = &ly->wgate; er = ffn; ec = dim; break;
+    case NL_WUP: mat = &ly->wup; er = ffn; ec = dim; break;
+    case NL_WDOWN: mat = &ly->wdown; er = dim; ec = ffn; break;
+    case NL_BQ: vec = &ly->bq; ec = qdim; break;
+    case NL_BK: vec = &ly->bk; ec = kvd; break;
+    case NL_BV: vec = &ly->bv; ec = kvd; break;
+    case NL_BO: vec = &ly->bo; ec = dim; break;
+    default: return fail(NL_ERR_INVALID, "unknown tensor slot %d", slot);
+    }
+    if (vec) {
+        if (rows * cols != ec) return fail(NL_ERR_INVALID, "slot %d: %lld elements, expected %lld", slot, (long long)(rows * cols), (long long)ec);
+        return upload_vec(vec, (int)type, ec, host, nbytes, m->st);
+    }
+    if (rows != er || cols != ec) return fail(NL_ERR_INVALID, "slot %d: shape %lldx%lld, expected %lldx%lld", slot, (long long)rows, (long long)cols, (long long)er, (long long)ec);
+    return upload_mat(*mat, (int)type, rows, cols, host, nbytes, m->st);
+}
+
+int nl_set_gamma(nl_model *m, const float *rows, int32_t n_rows, const int32_t *token_to_row) {
+    if (!m) return fail(NL_ERR_INVALID, "null argument");
+    int rc = set_dev(m); if (rc) return rc;
+    // graphs bake the gamma pointers in: drop them so the next forward re-captures
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    for (auto &g : m->g_fwd) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    for (auto &g : m->g_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (m->gamma) { cudaFree(m->gamma); m->gamma = nullptr; }
+    if (m->gamma_map) { cudaFree(m->gamma_map); m->gamma_map = nullptr; }
+    if (!rows) return NL_OK;
+    if (n_rows <= 0 || !token_to_row) return fail(NL_ERR_INVALID, "gamma: bad arguments");
+    NL_CUDA(cudaMalloc(&m->gamma, (size_t)n_rows * m->dim * 4));
+    NL_CUDA(cudaMalloc(&m->gamma_map, (size_t)m->c.vocab_size * 4));
+    NL_CUDA(cudaMemcpy(m->gamma, rows, (size_t)n_rows * m->dim * 4, cudaMemcpyHostToDevice));
+    NL_CUDA(cudaMemcpy(m->gamma_map, token_to_row, (size_t)m->c.vocab_size * 4, cudaMemcpyHostToDevice));
+    return NL_OK;
+}
+
+int nl_finalize(nl_model *m) {
+    if (!m) return fail(NL_ERR_INVALID, "null argument");
+    if (m->finalized) return NL_OK;
+    int rc = set_dev(m); if (rc) return rc;
+    const nl_config &c = m->c;
+    // every tensor loadWeights requires (go/model.go:177-265)
+    if (!m->tok_embd.present()) return fail(NL_ERR_STATE, "token_embd.weight: tensor not uploaded");
+    if (!m->output_norm) return fail(NL_ERR_STATE, "output_norm.weight: tensor not uploaded");
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        const char *miss = !ly.attn_norm ? "attn_norm" : !ly.ffn_norm ? "ffn_norm" : !ly.wq.present() ? "attn_q" : !ly.wk.present() ? "attn_k"
+                         : !ly.wv.present() ? "attn_v" : !ly.wo.present() ? "attn_output" : !ly.wgate.present() ? "ffn_gate"
+                         : !ly.wup.present() ? "ffn_up" : !ly.wdown.present() ? "ffn_down" : nullptr;
+        if (miss) return fail(NL_ERR_STATE, "layer %d %s: tensor not uploaded", l, miss);
+    }
+    const int B = m->B, dim = m->dim, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, half = m->hd / 2;
+    auto alloc = [&](float **p, size_t n) -> int { NL_CUDA(cudaMalloc(p, n * 4)); NL_CUDA(cudaMemset(*p, 0, n * 4)); return NL_OK; };
+    if ((rc = alloc(&m->x, (size_t)B * dim)) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, (size_t)B * qdim)) ||
+        (rc = alloc(&m->hb, (size_t)B * c.interm_size)) || (rc = alloc(&m->hb2, (size_t)B * c.interm_size)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
+        (rc = alloc(&m->k, (size_t)B * kvd)) || (rc = alloc(&m->v, (size_t)B * kvd)) || (rc = alloc(&m->logits, (size_t)B * c.vocab_size)) ||
+        (rc = alloc(&m->kc, (size_t)B * c.n_layers * S * kvd)) || (rc = alloc(&m->vc, (size_t)B * c.n_layers * S * kvd)))
+        return rc;
+    // RoPE tables: float64 pow/cos/sin rounded to fp32 (go/model.go:346-358)
+    std::vector<float> hc((size_t)S * half), hs((size_t)S * half);
+    const double theta = (double)c.rope_theta;
+    for (int pos = 0; pos < S; pos++)
+        for (int i = 0; i < half; i++) {
+            double freq = 1.0 / pow(theta, (double)(2 * i) / (double)m->hd);
+            double angle = (double)pos * freq;
+            hc[(size_t)pos * half + i] = (float)cos(angle);
+            hs[(size_t)pos * half + i] = (float)sin(angle);
+        }
+    NL_CUDA(cudaMalloc(&m->cos_t, hc.size() * 4)); NL_CUDA(cudaMalloc(&m->sin_t, hs.size() * 4));
+    NL_CUDA(cudaMemcpy(m->cos_t, hc.data(), hc.size() * 4, cudaMemcpyHostToDevice));
+    NL_CUDA(cudaMemcpy(m->sin_t, hs.data(), hs.size() * 4, cudaMemcpyHostToDevice));
+    m->gen_cap = S + 8; m->prompt_cap = S + 8;
+    NL_CUDA(cudaMalloc(&m->d_token, B * 4)); NL_CUDA(cudaMalloc(&m->d_pos, B * 4)); NL_CUDA(cudaMalloc(&m->d_gen_count, B * 4));
+    NL_CUDA(cudaMalloc(&m->d_gen, (size_t)B * m->gen_cap * 4)); NL_CUDA(cudaMalloc(&m->d_prompt, (size_t)m->prompt_cap * 4)); NL_CUDA(cudaMalloc(&m->d_cursor, 4));
+    NL_CUDA(cudaMemset(m->d_token, 0, B * 4)); NL_CUDA(cudaMemset(m->d_pos, 0, B * 4)); NL_CUDA(cudaMemset(m->d_gen_count, 0, B * 4)); NL_CUDA(cudaMemset(m->d_cursor, 0, 4));
+    NL_CUDA(cudaMallocHost(&m->h_stage, 2 * 64 * 4));
+    NL_CUDA(cudaMallocHost(&m->h_logits, (size_t)B * c.vocab_size * 4));
+    NL_CUDA(cudaEventCreate(&m->ev0)); NL_CUDA(cudaEventCreate(&m->ev1));
+    int64_t wb = m->tok_embd.bytes() + m->output.bytes() + (int64_t)dim * 4;
+    for (auto &ly : m->L) wb += ly.wq.bytes() + ly.wk.bytes() + ly.wv.bytes() + ly.wo.bytes() + ly.wgate.bytes() + ly.wup.bytes() + ly.wdown.bytes() + 2 * (int64_t)dim * 4;
+    m->weight_bytes = wb;
+    if (S * sizeof(float) > 48 * 1024) return fail(NL_ERR_INVALID, "seq_len too large for the attention kernel");
+    rc = build_graphs(m, 1);
+    if (rc) return rc;
+    m->finalized = true;
+    return NL_OK;
+}
+
+void nl_destroy(nl_model *m) {
+    if (!m) return;
+    cudaSetDevice(m->c.device);
+    if (m->st) cudaStreamSynchronize(m->st);
+    for (auto g : m->g_fwd) if (g) cudaGraphExecDestroy(g);
+    for (auto g : m->g_step) if (g) cudaGraphExecDestroy(g);
+    free_mat(m->tok_embd); free_mat(m->output);
+    for (auto &ly : m->L) {
+        free_mat(ly.wq); free_mat(ly.wk); free_mat(ly.wv); free_mat(ly.wo); free_mat(ly.wgate); free_mat(ly.wup); free_mat(ly.wdown);
+        cudaFree(ly.attn_norm); cudaFree(ly.ffn_norm); cudaFree(ly.bq); cudaFree(ly.bk); cudaFree(ly.bv); cudaFree(ly.bo);
+    }
+    float *fs[] = {m->output_norm, m->gamma, m->x, m->xb, m->xb2, m->hb, m->hb2, m->q, m->k, m->v, m->logits, m->kc, m->vc, m->cos_t, m->sin_t};
+    for (float *p : fs) if (p) cudaFree(p);
+    int32_t *is[] = {m->gamma_map, m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->d_prompt, m->d_cursor};
+    for (int32_t *p : is) if (p) cudaFree(p);
+    if (m->h_stage) cudaFreeHost(m->h_stage);
+    if (m->h_logits) cudaFreeHost(m->h_logits);
+    if (m->ev0) cudaEventDestroy(m->ev0);
+    if (m->ev1) cudaEventDestroy(m->ev1);
+    if (m->st) cudaStreamDestroy(m->st);
+    delete m;
+}
+
+static int ready(nl_model *m) {
+    if (!m) return fail(NL_ERR_INVALID, "null model");
+    if (!m->finalized) return fail(NL_ERR_STATE, "model not finalized");
+    return set_dev(m);
+}
+
+int nl_forward_batch(nl_model *m, int32_t B, const int32_t *tokens, const int32_t *pos, float *logits_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (B < 1 || B > m->B) return fail(NL_ERR_INVALID, "batch %d out of range [1,%d]", B, m->B);
+    if (!tokens || !pos) return fail(NL_ERR_INVALID, "null argument");
+    for (int b = 0; b < B; b++) {
+        // the Go engine would panic on the slice index; report instead
+        if (tokens[b] < 0 || tokens[b] >= m->c.vocab_size) return fail(NL_ERR_INVALID, "token %d out of range [0,%d)", tokens[b], m->c.vocab_size);
+        if (pos[b] < 0 || pos[b] >= m->c.seq_len) return fail(NL_ERR_INVALID, "pos %d out of range [0,%d)", pos[b], m->c.seq_len);
+    }
+    rc = build_graphs(m, B); if (rc) return rc;
+    memcpy(m->h_stage, tokens, B * 4); memcpy(m->h_stage + 64, pos, B * 4);
+    NL_CUDA(cudaMemcpyAsync(m->d_token, m->h_stage, B * 4, cudaMemcpyHostToDevice, m->st));
+    NL_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + 64, B * 4, cudaMemcpyHostToDevice, m->st));
+    NL_CUDA(cudaGraphLaunch(m->g_fwd[B], m->st));
+    if (logits_out) NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)B * m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    if (logits_out) memcpy(logits_out, m->h_logits, (size_t)B * m->c.vocab_size * 4);
+    return NL_OK;
+}
+
+int nl_forward(nl_model *m, int32_t token, int32_t pos, float *logits_out) { return nl_forward_batch(m, 1, &token, &pos, logits_out); }
+
+int nl_get_logits(nl_model *m, float *logits_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (!logits_out) return fail(NL_ERR_INVALID, "null argument");
+    NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    memcpy(logits_out, m->h_logits, (size_t)m->c.vocab_size * 4);
+    return NL_OK;
+}
+
+int nl_reset(nl_model *m) {
+    int rc = ready(m); if (rc) return rc;
+    size_t n = (size_t)m->B * m->c.n_layers * m->c.seq_len * m->kvd * 4;
+    NL_CUDA(cudaMemsetAsync(m->kc, 0, n, m->st));
+    NL_CUDA(cudaMemsetAsync(m->vc, 0, n, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    return NL_OK;
+}
+
+// token-by-token prefill of sequence 0 on the device (feed kernel + forward graph per token)
+static int prefill_sequential(nl_model *m, const int32_t *tokens, int n, int pos0) {
+    if (n > m->prompt_cap) return fail(NL_ERR_INVALID, "prompt too long");
+    NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, m->st));
+    NL_CUDA(cudaMemsetAsync(m->d_cursor, 0, 4, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));  // tokens is caller memory: the copy must be done before we return or reuse it
+    for (int i = 0; i < n; i++) {
+        feed_prompt_kernel<<<1, 1, 0, m->st>>>(m->d_prompt, m->d_cursor, pos0, m->d_token, m->d_pos);
+        NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
+    }
+    NL_CUDA(cudaGetLastError());
+    return NL_OK;
+}
+
+int nl_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *logits_last) {
+    int rc = ready(m); if (rc) return rc;
+    if (!tokens || n <= 0) return fail(NL_ERR_INVALID, "empty prompt");
+    if (pos0 < 0 || pos0 + n > m->c.seq_len) return fail(NL_ERR_INVALID, "positions [%d,%d) exceed seq_len %d", pos0, pos0 + n, m->c.seq_len);
+    for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m->c.vocab_size) return fail(NL_ERR_INVALID, "token %d out of range", tokens[i]);
+    rc = prefill_sequential(m, tokens, n, pos0); if (rc) return rc;
+    if (logits_last) NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    if (logits_last) memcpy(logits_last, m->h_logits, (size_t)m->c.vocab_size * 4);
+    return NL_OK;
+}
+
+int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int32_t n_new, int32_t eos_id, int32_t *out_tokens, int32_t *n_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (!prompt || n_prompt <= 0 || !out_tokens || !n_out || n_new < 0) return fail(NL_ERR_INVALID, "bad argument");
+    for (int i = 0; i < n_prompt; i++) if (prompt[i] < 0 || prompt[i] >= m->c.vocab_size) return fail(NL_ERR_INVALID, "token %d out of range", prompt[i]);
+    *n_out = 0;
+    const int S = m->c.seq_len;
+    rc = nl_reset(m); if (rc) return rc;                         // go/main.go:156
+    int n_fed = n_prompt < S - 1 ? n_prompt : S - 1;             // prefill stops at seq_len-1, go/main.go:160-166
+    if (n_fed < 1) n_fed = 1;
+    rc = prefill_sequential(m, prompt, n_fed, 0); if (rc) return rc;
+    int pos = n_fed;
+    NL_CUDA(cudaMemsetAsync(m->d_gen_count, 0, 4, m->st));
+    // each step: sample (argmax), then Forward(next, pos), pos++, stop when pos >= seq_len (go/main.go:173-218).
+    // EOS is only visible on the host, so run in chunks and trim.
+    int produced = 0; bool done = false;
+    std::vector<int32_t> chunk(64);
+    while (produced < n_new && !done) {
+        int steps = n_new - produced < 64 ? n_new - produced : 64;
+        int run = 0;
+        for (int i = 0; i < steps; i++) {
+            if (pos >= S) {  // the reference samples one last token, then Forward would overflow: it breaks after Forward at pos==S-1
+                break;
+            }
+            NL_CUDA(cudaGraphLaunch(m->g_step[1], m->st));
+            pos++; run++;
+        }
+        if (run == 0) break;
+        NL_CUDA(cudaMemcpyAsync(chunk.data(), m->d_gen + produced, (size_t)run * 4, cudaMemcpyDeviceToHost, m->st));
+        NL_CUDA(cudaStreamSynchronize(m->st));
+        for (int i = 0; i < run; i++) {
+            out_tokens[produced++] = chunk[i];
+            if (eos_id >= 0 && chunk[i] == eos_id) { done = true; break; }
+        }
+        if (pos >= S) done = true;
+    }
+    *n_out = produced;
+    return NL_OK;
+}
+
+int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, float *ms_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (!ms_out || n_steps <= 0 || pos0 < 0 || pos0 + n_steps > m->c.seq_len || token < 0 || token >= m->c.vocab_size) return fail(NL_ERR_INVALID, "bad argument");
+    int32_t p = pos0 - 1;  // argmax_advance pre-increments
+    // seed: logits currently on the device decide the first token unless we overwrite; do one plain forward first
+    m->h_stage[0] = token; m->h_stage[64] = pos0;
+    NL_CUDA(cudaMemcpyAsync(m->d_token, m->h_stage, 4, cudaMemcpyHostToDevice, m->st));
+    NL_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + 64, 4, cudaMemcpyHostToDevice, m->st));
+    NL_CUDA(cudaMemsetAsync(m->d_gen_count, 0, 4, m->st));
+    (void)p;
+    NL_CUDA(cudaEventRecord(m->ev0, m->st));
+    NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
+    for (int i = 1; i < n_steps; i++) NL_CUDA(cudaGraphLaunch(m->g_step[1], m->st));
+    NL_CUDA(cudaEventRecord(m->ev1, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
+    return NL_OK;
+}
+
+int nl_launches_per_token(const nl_model *m) { return m ? m->launches_fwd + 1 : 0; }
+int64_t nl_weight_bytes(const nl_model *m) { return m ? m->weight_bytes : 0; }
+
+// ---- operator-level hooks ----
+int nl_dequant(uint32_t type, const void *host_src, int64_t n, float *host_dst) {
+    if (!host_src || !host_dst || n <= 0) return fail(NL_ERR_INVALID, "bad argument");
+    if (!type_supported((int)type)) return fail(NL_ERR_UNSUPPORTED, "unsupported tensor type %u", type);
+    int be = blk_elems((int)type);
+    if (n % be) return fail(NL_ERR_INVALID, "n=%lld not a multiple of the block size %d", (long long)n, be);
+    int dev = 0; cudaGetDevice(&dev);
+    int rc = check_device(dev); if (rc) return rc;
+    // present the data as a [n/be', be'] matrix so the F16/F32 unit constraints hold for any n
+    DevMat m;
+    int64_t cols = be == 1 ? 1 : be; int64_t rows = n / cols;
+    m.type = (int)type;
+    size_t nbytes = (size_t)tensor_nbytes((int)type, n);
+    if (type == NL_F16 || type == NL_F32) {  // bypass the 16-byte-unit check of upload_mat (no GEMV on this path)
+        m.rows = rows; m.cols = cols; m.qs_bytes = nbytes;
+        NL_CUDA(cudaMalloc(&m.qs, nbytes));
+        NL_CUDA(cudaMemcpy(m.qs, host_src, nbytes, cudaMemcpyHostToDevice));
+    } else {
+        rc = upload_mat(m, (int)type, rows, cols, host_src, nbytes, 0); if (rc) return rc;
+    }
+    float *out = nullptr;
+    cudaError_t e = cudaMalloc(&out, (size_t)n * 4);
+    if (e != cudaSuccess) { free_mat(m); return fail(NL_ERR_OOM, "cudaMalloc: %s", cudaGetErrorString(e)); }
+    rc = dequant_mat(m, out, 0);
+    if (!rc) { e = cudaMemcpy(host_dst, out, (size_t)n * 4, cudaMemcpyDeviceToHost); if (e != cudaSuccess) rc = fail(NL_ERR_CUDA, "D2H: %s", cudaGetErrorString(e)); }
+    cudaFree(out); free_mat(m);
+    return rc;
+}
+
+struct nl_matrix {
+    int device = 0;
+    std::vector<DevMat> copies;  // replicas for L2-cold benchmarking; [0] is the matrix
+    float *x = nullptr, *out = nullptr; int xcap = 0;
+    cudaStream_t st = nullptr;
+};
+
+int nl_matrix_create(uint32_t type, const void *host_w, int64_t rows, int64_t cols, int32_t device, nl_matrix **out) {
+    if (!host_w || !out) return fail(NL_ERR_INVALID, "null argument");
+    *out = nullptr;
+    int rc = check_device(device); if (rc) return rc;
+    if (rows > INT32_MAX || cols > INT32_MAX) return fail(NL_ERR_INVALID, "matrix too large");
+    nl_matrix *w = new nl_matrix(); w->device = device; w->copies.resize(1);
+    cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking);
+    int64_t nb = tensor_nbytes((int)type, rows * cols);
+    rc = upload_mat(w->copies[0], (int)type, rows, cols, host_w, nb < 0 ? 0 : (size_t)nb, w->st);
+    if (rc) { nl_matrix_destroy(w); return rc; }
+    *out = w;
+    return NL_OK;
+}
+
+static int matrix_buffers(nl_matrix *w, int batch) {
+    if (batch <= w->xcap) return NL_OK;
+    if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
+    w->x = w->out = nullptr;
+    NL_CUDA(cudaMalloc(&w->x, (size_t)batch * w->copies[0].cols * 4));
+    NL_CUDA(cudaMalloc(&w->out, (size_t)batch * w->copies[0].rows * 4));
+    w->xcap = batch;
+    return NL_OK;
+}
+
+int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *host_out) {
+    if (!w || !host_x || !host_out || batch < 1 || batch > 64) return fail(NL_ERR_INVALID, "bad argument");
+    NL_CUDA(cudaSetDevice(w->device));
+    int rc = matrix_buffers(w, batch); if (rc) return rc;
+    const DevMat &m = w->copies[0];
+    NL_CUDA(cudaMemcpyAsync(w->x, host_x, (size_t)batch * m.cols * 4, cudaMemcpyHostToDevice, w->st));
+    MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
+    rc = gemv_multi(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, w->st); if (rc) return rc;
+    NL_CUDA(cudaMemcpyAsync(host_out, w->out, (size_t)batch * m.rows * 4, cudaMemcpyDeviceToHost, w->st));
+    NL_CUDA(cudaStreamSynchronize(w->st));
+    return NL_OK;
+}
+
+int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmup, int32_t iters, float *ms_out) {
+    if (!w || !ms_out || batch < 1 || batch > 64 || n_copies < 1 || iters < 1) return fail(NL_ERR_INVALID, "bad argument");
+    NL_CUDA(cudaSetDevice(w->device));
+    int rc = matrix_buffers(w, batch); if (rc) return rc;
+    const DevMat src = w->copies[0];
+    while ((int)w->copies.size() < n_copies) {
+        DevMat c = src; c.qs = nullptr; c.d = nullptr;
+        NL_CUDA(cudaMalloc(&c.qs, src.qs_bytes));
+        NL_CUDA(cudaMemcpy(c.qs, src.qs, src.qs_bytes, cudaMemcpyDeviceToDevice));
+        if (src.d) { NL_CUDA(cudaMalloc(&c.d, src.d_bytes)); NL_CUDA(cudaMemcpy(c.d, src.d, src.d_bytes, cudaMemcpyDeviceToDevice)); }
+        w->copies.push_back(c);
+    }
+    NL_CUDA(cudaMemsetAsync(w->x, 0, (size_t)batch * src.cols * 4, w->st));
+    cudaEvent_t e0, e1; NL_CUDA(cudaEventCreate(&e0)); NL_CUDA(cudaEventCreate(&e1));
+    int idx = 0;
+    for (int i = 0; i < warmup + iters; i++) {
+        if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));
+        MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
+        rc = gemv_multi(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, w->st); if (rc) return rc;
+        idx = (idx + 1) % n_copies;
+    }
+    NL_CUDA(cudaEventRecord(e1, w->st));
+    NL_CUDA(cudaStreamSynchronize(w->st));
+    float ms = 0; NL_CUDA(cudaEventElapsedTime(&ms, e0, e1));
+    cudaEventDestroy(e0); cudaEventDestroy(e1);
+    *ms_out = ms / iters;
+    return NL_OK;
+}
+
+void nl_matrix_destroy(nl_matrix *w) {
+    if (!w) return;
+    cudaSetDevice(w->device);
+    if (w->st) cudaStreamSynchronize(w->st);
+    for (auto &c : w->copies) free_mat(c);
+    if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
+    if (w->st) cudaStreamDestroy(w->st);
+    delete w;
+}
+
+int nl_matmul(uint32_t type, const void *host_w, int64_t rows, int64_t cols, const float *host_x, int32_t batch, float *host_out) {
+    int dev = 0; cudaGetDevice(&dev);
+    nl_matrix *w = nullptr;
+    int rc = nl_matrix_create(type, host_w, rows, cols, dev, &w); if (rc) return rc;
+    rc = nl_matrix_matmul(w, host_x, batch, host_out);
+    nl_matrix_destroy(w);
+    return rc;
+}
+
+int nl_tp_export_handle(nl_model *m, void *handle64) { (void)m; (void)handle64; return fail(NL_ERR_UNSUPPORTED, "tensor parallelism is not built yet"); }
+int nl_tp_import_handles(nl_model *m, const void *h, int32_t n) { (void)m; (void)h; (void)n; return fail(NL_ERR_UNSUPPORTED, "tensor parallelism is not built yet"); }
+
+}  // extern "C"

@@ -1,0 +1,88 @@
+// nl_common.cuh — shared types/helpers for libnanollama_cuda.so (sm_100a only).
+#pragma once
+#include <cuda_fp16.h>
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+#include <string>
+
+#include "../../include/nanollama_cuda.h"
+
+namespace nl {
+
+// ---- error plumbing (thread-local message behind nl_last_error) ----
+void set_error(const char *fmt, ...);
+int fail(int code, const char *fmt, ...);
+
+#define NL_CUDA(expr)                                                                                   \
+    do {                                                                                                \
+        cudaError_t _e = (expr);                                                                        \
+        if (_e != cudaSuccess) return nl::fail(NL_ERR_CUDA, "%s: %s (%s:%d)", #expr, cudaGetErrorString(_e), __FILE__, __LINE__); \
+    } while (0)
+
+// ---- GGML block geometry (go/gguf.go:238-272) ----
+__host__ __device__ inline int blk_elems(int t) { return (t == NL_F32 || t == NL_F16) ? 1 : (t == NL_Q4_K || t == NL_Q6_K) ? 256 : 32; }
+__host__ __device__ inline int blk_bytes(int t) {
+    switch (t) {
+    case NL_F32: return 4; case NL_F16: return 2; case NL_Q4_0: return 18; case NL_Q5_0: return 22;
+    case NL_Q8_0: return 34; case NL_Q4_K: return 144; case NL_Q6_K: return 210; default: return 0;
+    }
+}
+inline int64_t tensor_nbytes(int t, int64_t n) { return blk_bytes(t) ? n / blk_elems(t) * blk_bytes(t) : -1; }
+
+// ---- device-resident weight matrix in the library's planar layout ----
+// The 18-B / 34-B GGUF blocks are only 2-B aligned, so at upload each matrix is split (bijectively) into
+//   qs : [rows][cols/32] x 16 B (Q4_0 nibbles, byte j = elem j | elem j+16 << 4)  or  32 B (Q8_0 int8)
+//   d  : [rows][cols/32] fp16 block scales
+// Same bytes as the GGUF tensor, now 16-B aligned for 128-bit loads / bulk copies.  F16/F32 are kept as they are.
+// Q5_0/Q4_K/Q6_K are kept in raw GGUF block order (qs = raw bytes).
+struct DevMat {
+    int type = -1;
+    int64_t rows = 0, cols = 0;
+    uint8_t *qs = nullptr;
+    __half *d = nullptr;
+    size_t qs_bytes = 0, d_bytes = 0;
+    bool present() const { return qs != nullptr; }
+    size_t bytes() const { return qs_bytes + d_bytes; }
+};
+
+// ---- small device helpers ----
+__device__ __forceinline__ float warp_sum(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ double warp_sum_d(double v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    return v;
+}
+__device__ __forceinline__ float warp_max(float v) {
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) v = fmaxf(v, __shfl_xor_sync(0xffffffffu, v, o));
+    return v;
+}
+// streaming 128-/64-bit loads that do not pollute L1 (weights are read once per token)
+__device__ __forceinline__ uint4 ldg_stream_u4(const void *p) {
+    uint4 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ uint2 ldg_stream_u2(const void *p) {
+    uint2 r;
+    asm volatile("ld.global.nc.L1::no_allocate.v2.u32 {%0,%1}, [%2];" : "=r"(r.x), "=r"(r.y) : "l"(p));
+    return r;
+}
+__device__ __forceinline__ unsigned short ldg_stream_u16(const void *p) {
+    unsigned short r;
+    asm volatile("ld.global.nc.L1::no_allocate.u16 %0, [%1];" : "=h"(r) : "l"(p));
+    return r;
+}
+// exact small-int -> fp32 without I2F: 0x4B000000|n is 2^23+n
+__device__ __forceinline__ float u8_to_f32_magic(uint32_t word, int byte_idx) {
+    return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | byte_idx));
+}
+
+__device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }  // go/quant.go:629-631
+
+}  // namespace nl

@@ -1,0 +1,5 @@
+// dequant-fused GEMV instantiations for NL_F32 weights (see nl_kernels.cuh / nl_gemv.cuh)
+#include "nl_gemv.cuh"
+namespace nl {
+int launch_gemv_f32(const GemvArgs &a, int batch, int epi, cudaStream_t st) { return launch_gemv_typed<NL_F32>(a, batch, epi, st); }
+}  // namespace nl

@@ -1,0 +1,5 @@
+// dequant-fused GEMV instantiations for NL_Q8_0 weights (see nl_kernels.cuh / nl_gemv.cuh)
+#include "nl_gemv.cuh"
+namespace nl {
+int launch_gemv_q8_0(const GemvArgs &a, int batch, int epi, cudaStream_t st) { return launch_gemv_typed<NL_Q8_0>(a, batch, epi, st); }
+}  // namespace nl

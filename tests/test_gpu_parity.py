@@ -1,0 +1,310 @@
+"""Parity of the CUDA path (through the C ABI) with the CPU oracle and the reference-made golden fixtures.
+Run on the B200 box: python -m pytest tests -m gpu.
+Tolerances: dequant bit-exact; matmul / logits max-rel <= 1e-3 per BASELINE.json (observed ~1e-6); greedy streams identical."""
+import os
+
+import numpy as np
+import pytest
+
+from nanollama_b200 import gguf as G
+from nanollama_b200 import model as M
+from nanollama_b200 import tiers as T
+from oracle import oracle as O
+
+pytestmark = pytest.mark.gpu
+
+LOGIT_TOL = 1e-3  # BASELINE.json north_star: max relative error of logits, fp32 accumulate
+
+
+def maxrel(a, b):
+    return float(np.abs(a - b).max() / max(np.abs(b).max(), 1e-30))
+
+
+@pytest.fixture(scope="module")
+def kat(golden_dir):
+    return np.load(os.path.join(golden_dir, "dequant_kat.npz"))
+
+
+@pytest.fixture(scope="module")
+def gold(golden_dir):
+    return np.load(os.path.join(golden_dir, "golden_logits.npz"))
+
+
+# ---------------------------------------------------------------- dequant: bit-exact
+@pytest.mark.parametrize("key,typ", [("q4_0", G.GGML_Q4_0), ("q8_0", G.GGML_Q8_0), ("q8_0_requant", G.GGML_Q8_0), ("f16", G.GGML_F16)])
+def test_dequant_golden_bit_exact(kat, key, typ):
+    got = M.dequant(typ, kat[key + "_bytes"], 2048).view(np.uint32)
+    assert np.array_equal(got, kat[key + "_expect"])
+
+
+def test_half2float_all_bit_patterns(kat):
+    allh = np.arange(65536, dtype=np.uint16)
+    got = M.dequant(G.GGML_F16, allh.view(np.uint8), 65536).view(np.uint32)
+    exp = kat["half_all_expect"]
+    # cvt.f32.f16 quiets signalling NaNs; every other pattern (subnormals, infs, quiet NaN payloads) is identical
+    h = allh
+    snan = ((h & 0x7C00) == 0x7C00) & ((h & 0x03FF) != 0) & ((h & 0x0200) == 0)
+    assert np.array_equal(got[~snan], exp[~snan])
+    assert np.all(np.isnan(got[snan].view(np.float32)))
+
+
+@pytest.mark.parametrize("typ", [G.GGML_Q4_0, G.GGML_Q8_0, G.GGML_F16, G.GGML_F32, G.GGML_Q5_0, G.GGML_Q4_K, G.GGML_Q6_K])
+def test_dequant_random_bytes_bit_exact_vs_oracle(typ):
+    rng = np.random.default_rng(typ)
+    n = 256 * 37
+    nbytes = n // G.ggml_block_elements(typ) * G.ggml_block_size(typ)
+    raw = rng.integers(0, 256, size=nbytes, dtype=np.uint8)
+    # keep fp16 scale fields finite (random bytes hit inf/NaN exponents; NaN payload propagation through a multiply is
+    # not something the Go engine defines either)
+    bs = G.ggml_block_size(typ)
+    blocks = raw.reshape(-1, bs) if typ not in (G.GGML_F16, G.GGML_F32) else None
+    if typ in (G.GGML_Q4_0, G.GGML_Q8_0, G.GGML_Q5_0):
+        blocks[:, 1] &= 0x7B
+    elif typ == G.GGML_Q4_K:
+        blocks[:, 1] &= 0x7B; blocks[:, 3] &= 0x7B
+    elif typ == G.GGML_Q6_K:
+        blocks[:, 209] &= 0x7B
+    elif typ == G.GGML_F16:
+        raw[1::2] &= 0x7B
+    elif typ == G.GGML_F32:
+        raw[3::4] &= 0x7E
+    got = M.dequant(typ, raw, n).view(np.uint32)
+    exp = O.dequant(typ, raw, n).view(np.uint32)
+    assert np.array_equal(got, exp)
+
+
+def test_dequant_unsupported_type():
+    with pytest.raises(Exception, match="unsupported"):
+        M.dequant(3, np.zeros(20, np.uint8), 32)
+
+
+# ---------------------------------------------------------------- matmulDispatch
+SHAPES = [(576, 576), (1536, 576), (576, 1536), (192, 768), (2048, 768), (768, 2048), (1000, 768), (7, 64), (4096, 1536)]
+
+
+@pytest.mark.parametrize("typ", [G.GGML_Q4_0, G.GGML_Q8_0, G.GGML_F16, G.GGML_F32])
+@pytest.mark.parametrize("rows,cols", SHAPES)
+def test_matmul_vs_oracle(typ, rows, cols):
+    rng = np.random.default_rng(rows * 31 + cols + typ)
+    w = (rng.standard_normal((rows, cols)) / np.sqrt(cols)).astype(np.float32)
+    raw = G.encode_tensor(w, typ)
+    x = rng.standard_normal(cols).astype(np.float32)
+    got = M.matmul_dispatch(raw, typ, x, rows, cols)
+    exp = O.matmul(raw, typ, x, rows, cols)
+    assert maxrel(got, exp) < 1e-5
+
+
+@pytest.mark.parametrize("typ", [G.GGML_Q5_0, G.GGML_Q4_K, G.GGML_Q6_K])
+def test_matmul_kquants_vs_oracle(typ):
+    rng = np.random.default_rng(typ)
+    rows, cols = 96, 1024
+    nbytes = rows * cols // G.ggml_block_elements(typ) * G.ggml_block_size(typ)
+    raw = rng.integers(0, 256, size=nbytes, dtype=np.uint8)
+    blocks = raw.reshape(-1, G.ggml_block_size(typ))
+    for col in {G.GGML_Q5_0: [1], G.GGML_Q4_K: [1, 3], G.GGML_Q6_K: [209]}[typ]:
+        blocks[:, col] = (blocks[:, col] & 0x03) | 0x28  # modest fp16 scales
+    x = rng.standard_normal(cols).astype(np.float32)
+    got = M.matmul_dispatch(raw, typ, x, rows, cols)
+    exp = O.matmul(raw, typ, x, rows, cols)
+    assert maxrel(got, exp) < 1e-5
+
+
+@pytest.mark.parametrize("batch", [2, 3, 4, 5, 8])
+def test_matmul_small_batch(batch):
+    rng = np.random.default_rng(batch)
+    rows, cols = 1536, 576
+    raw = G.quantize_q4_0((rng.standard_normal((rows, cols)) / 24).astype(np.float32))
+    x = rng.standard_normal((batch, cols)).astype(np.float32)
+    dm = M.DeviceMatrix(raw, G.GGML_Q4_0, rows, cols)
+    got = dm.matmul(x)
+    for b in range(batch):
+        assert maxrel(got[b], O.matmul(raw, G.GGML_Q4_0, x[b], rows, cols)) < 1e-5
+    # linearity (size-independent property): W(a*x0 + x1) == a*W x0 + W x1
+    y = dm.matmul(2.0 * x[0] + x[1])
+    assert maxrel(y, 2.0 * got[0] + got[1]) < 1e-5
+
+
+def test_matmul_zero_and_shape_errors():
+    raw = G.quantize_q8_0(np.zeros((8, 64), np.float32))
+    assert np.array_equal(M.matmul_dispatch(raw, G.GGML_Q8_0, np.ones(64, np.float32), 8, 64), np.zeros(8, np.float32))
+    with pytest.raises(Exception):
+        M.matmul_dispatch(raw, G.GGML_Q8_0, np.ones(48, np.float32), 8, 48)  # cols % 32 != 0
+    with pytest.raises(Exception):
+        M.matmul_dispatch(raw[:-1], G.GGML_Q8_0, np.ones(64, np.float32), 8, 64)
+
+
+# ---------------------------------------------------------------- Forward
+FILES = ["tiny_gqa_f16", "tiny_gqa_q8_0", "tiny_gqa_q8_0_requant", "tiny_gqa_q4_0", "tiny_mha_qknorm_q8_0"]
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_forward_logits_vs_oracle_and_reference_golden(golden_dir, gold, name):
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    m.reset(); o.reset()
+    for pos, t in enumerate(gold["tokens"]):
+        m.forward(int(t), pos)
+        exp = o.forward(int(t), pos)
+        assert maxrel(m.state.logits, exp) < LOGIT_TOL
+        assert maxrel(m.state.logits, exp) < 2e-5           # what fp32 reassociation actually costs
+        assert maxrel(m.state.logits, gold[name + "_logits"][pos]) < LOGIT_TOL
+        assert int(np.argmax(m.state.logits)) == int(np.argmax(exp))
+    m.close()
+
+
+@pytest.mark.parametrize("conj,qkn", [(True, False), (True, True), (False, True)])
+def test_forward_flag_variants_vs_oracle(golden_dir, gold, conj, qkn):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q4_0.gguf"))
+    m = M.load_llama_model(gf, rope_conjugate=conj, qk_norm=qkn)
+    o = O.OracleModel(gf, rope_conjugate=conj, qk_norm=qkn)
+    for pos, t in enumerate(gold["tokens"]):
+        m.forward(int(t), pos)
+        assert maxrel(m.state.logits, o.forward(int(t), pos)) < 2e-5
+    m.close()
+
+
+@pytest.mark.parametrize("name", FILES)
+def test_greedy_stream_identical(golden_dir, gold, name):
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    prompt = gold["tokens"][:8]
+    exp, margins = o.generate_greedy(prompt, 56)
+    got = m.generate_greedy(prompt, 56)
+    assert len(got) == len(exp) == 56  # 8 + 56 = seq_len 64: runs to the context end
+    bad = [i for i in range(56) if got[i] != exp[i]]
+    assert not bad or margins[bad[0]] < 1e-5, (bad[:3], margins[bad[0]] if bad else None)
+    m.close()
+
+
+def test_generate_stops_like_reference(golden_dir, gold):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    prompt = gold["tokens"][:8]
+    exp, _ = o.generate_greedy(prompt, 200)          # context (64) ends first
+    got = m.generate_greedy(prompt, 200)
+    assert len(got) == len(exp) and np.array_equal(got, exp)
+    eos = int(exp[5])                                 # pretend the 6th generated token is EOS
+    exp2, _ = o.generate_greedy(prompt, 200, eos_id=eos)
+    got2 = m.generate_greedy(prompt, 200, eos_id=eos)
+    assert np.array_equal(got2, exp2) and got2[-1] == eos
+    long_prompt = np.resize(gold["tokens"], 100)      # longer than the context: prefill stops at seq_len-1
+    exp3, _ = o.generate_greedy(long_prompt, 10)
+    got3 = m.generate_greedy(long_prompt, 10)
+    assert np.array_equal(got3, exp3) and len(got3) == 1
+    m.close()
+
+
+def test_reset_and_replay(golden_dir, gold):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q4_0.gguf"))
+    m = M.load_llama_model(gf)
+    toks = gold["tokens"]
+    for pos, t in enumerate(toks):
+        m.forward(int(t), pos)
+    first = m.state.logits.copy()
+    m.reset()
+    for pos, t in enumerate(toks):
+        m.forward(int(t), pos)
+    assert np.array_equal(first, m.state.logits)      # deterministic, and Reset really clears state
+    m.prefill(toks)                                   # one-call prefill == token-by-token
+    assert maxrel(m.state.logits, first) < 1e-6
+    m.close()
+
+
+def test_forward_errors(golden_dir):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = M.load_llama_model(gf)
+    with pytest.raises(IndexError):
+        m.forward(256, 0)
+    with pytest.raises(IndexError):
+        m.forward(-1, 0)
+    with pytest.raises(IndexError):
+        m.forward(1, 64)
+    m.close()
+
+    class Missing:
+        meta = gf.meta
+        def get_tensor(self, name):
+            if name == "blk.1.ffn_up.weight":
+                raise KeyError(f"tensor not found: {name}")
+            return gf.get_tensor(name)
+    with pytest.raises(RuntimeError, match="load weights:.*blk.1.ffn_up.weight"):
+        M.load_llama_model(Missing())
+
+
+def test_tied_embeddings_fallback(golden_dir, gold):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+
+    class Tied:
+        meta = gf.meta
+        tensors = {k: v for k, v in gf.tensors.items() if k != "output.weight"}
+        def get_tensor(self, name):
+            if name == "output.weight":
+                raise KeyError(f"tensor not found: {name}")
+            return gf.get_tensor(name)
+    m = M.load_llama_model(Tied())
+    o = O.OracleModel(Tied())
+    for pos, t in enumerate(gold["tokens"][:6]):
+        m.forward(int(t), pos)
+        assert maxrel(m.state.logits, o.forward(int(t), pos)) < 2e-5
+    m.close()
+
+
+def test_batch_forward_matches_single(golden_dir, gold):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q4_0.gguf"))
+    m1 = M.load_llama_model(gf)
+    mb = M.load_llama_model(gf, max_batch=3)
+    toks = gold["tokens"]
+    seqs = [toks[:10], toks[3:13], toks[5:15]]
+    singles = []
+    for s in seqs:
+        m1.reset()
+        for pos, t in enumerate(s):
+            m1.forward(int(t), pos)
+        singles.append(m1.state.logits.copy())
+    for pos in range(10):
+        out = mb.forward_batch([int(s[pos]) for s in seqs], [pos] * 3)
+    for b in range(3):
+        assert maxrel(out[b], singles[b]) < 1e-5
+    m1.close(); mb.close()
+
+
+def test_gamma_injection(golden_dir, gold):
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(3)
+    rows = (0.05 * rng.standard_normal((4, 128))).astype(np.float32)
+    mp = np.full(256, -1, np.int32)
+    toks = gold["tokens"]
+    mp[int(toks[1])] = 0; mp[int(toks[2])] = 3
+    m.set_gamma(rows, mp); o.set_gamma(rows, mp)
+    for pos, t in enumerate(toks[:5]):
+        m.forward(int(t), pos)
+        assert maxrel(m.state.logits, o.forward(int(t), pos)) < 2e-5
+    m.close()
+
+
+# ---------------------------------------------------------------- BASELINE.json configs 1 and 2
+@pytest.mark.parametrize("tier,typ,n_new", [("nano", G.GGML_Q8_0, 256), ("mini", G.GGML_Q8_0, 256), ("mini", G.GGML_Q4_0, 256)])
+def test_tier_greedy_256_identical(tier, typ, n_new):
+    """Random-init tier -> 16-token prompt -> 256 greedy tokens: identical stream, logits within 1e-3 (BASELINE north_star)."""
+    gf = T.SyntheticGGUF(tier, typ, seed=1, seq_len=512)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(11)
+    prompt = np.concatenate([[1], rng.integers(3, gf.meta.vocab_size, size=15)]).astype(np.int32)
+    exp, margins = o.generate_greedy(prompt, n_new)
+    got = m.generate_greedy(prompt, n_new)
+    assert len(got) == len(exp) == n_new
+    bad = [i for i in range(n_new) if got[i] != exp[i]]
+    assert not bad or margins[bad[0]] < 1e-4, (bad[:3], float(margins[bad[0]]) if bad else None, float(margins.min()))
+    # logits at the end of the run (position 16+255) against the oracle's
+    m.reset(); o.reset()
+    seq = np.concatenate([prompt, exp[:-1]])
+    for pos in (0, 1, 2):
+        m.forward(int(seq[pos]), pos)
+        assert maxrel(m.state.logits, o.forward(int(seq[pos]), pos)) < LOGIT_TOL
+    m.close()
