@@ -83,6 +83,15 @@ __device__ __forceinline__ float u8_to_f32_magic(uint32_t word, int byte_idx) {
     return __uint_as_float(__byte_perm(word, 0x4B000000u, 0x7540u | byte_idx));
 }
 
+// binary16 -> binary32 with the exact semantics of the reference's 65,536-entry table (go/gguf.go:601-636): NaNs keep their
+// payload (mant << 13) instead of being canonicalised the way cvt.f32.f16 does.  Used where bit-exactness is the contract
+// (dequant, embedding rows); the GEMV inner loops use the plain conversion (identical for every non-NaN input).
+__device__ __forceinline__ float h2f_exact(unsigned short h) {
+    if ((h & 0x7C00u) == 0x7C00u) return __uint_as_float(((uint32_t)(h & 0x8000u) << 16) | 0x7F800000u | ((uint32_t)(h & 0x03FFu) << 13));
+    return __half2float(__ushort_as_half(h));
+}
+__device__ __forceinline__ float h2f_exact(__half h) { return h2f_exact(__half_as_ushort(h)); }
+
 __device__ __forceinline__ float silu_f(float x) { return x / (1.0f + expf(-x)); }  // go/quant.go:629-631
 
 }  // namespace nl

@@ -45,7 +45,7 @@ static __global__ void repack_q8_0_kernel(const uint8_t *__restrict__ raw, uint4
 static __global__ void dequant_q4_0_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ d, float *__restrict__ out, int64_t nblocks) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    float s = __half2float(d[b]);
+    float s = h2f_exact(d[b]);
     uint4 q = qs[b];
     uint32_t w[4] = {q.x, q.y, q.z, q.w};
     float *o = out + b * 32;
@@ -61,7 +61,7 @@ static __global__ void dequant_q4_0_kernel(const uint4 *__restrict__ qs, const _
 static __global__ void dequant_q8_0_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ d, float *__restrict__ out, int64_t nblocks) {
     int64_t b = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
     if (b >= nblocks) return;
-    float s = __half2float(d[b]);
+    float s = h2f_exact(d[b]);
     float *o = out + b * 32;
 #pragma unroll
     for (int h = 0; h < 2; h++) {
@@ -75,10 +75,10 @@ static __global__ void dequant_q8_0_kernel(const uint4 *__restrict__ qs, const _
 }
 static __global__ void dequant_f16_kernel(const __half *__restrict__ src, float *__restrict__ out, int64_t n) {
     int64_t i = (int64_t)blockIdx.x * blockDim.x + threadIdx.x;
-    if (i < n) out[i] = __half2float(src[i]);
+    if (i < n) out[i] = h2f_exact(src[i]);
 }
 // raw-block types (the "next" row of SURVEY §8f): go/quant.go:405-420 (Q5_0), :296-323 (Q4_K), :174-208 (Q6_K)
-__device__ __forceinline__ float h2f_raw(const uint8_t *p) { return __half2float(__ushort_as_half((unsigned short)(p[0] | (p[1] << 8)))); }
+__device__ __forceinline__ float h2f_raw(const uint8_t *p) { return h2f_exact((unsigned short)(p[0] | (p[1] << 8))); }
 __device__ __forceinline__ void scale_min_k4(int j, const uint8_t *s, int &sc, int &m) {
     if (j < 4) { sc = s[j] & 63; m = s[j + 4] & 63; }
     else { sc = (s[j + 4] & 0x0F) | ((s[j - 4] >> 6) << 4); m = (s[j + 4] >> 4) | ((s[j] >> 6) << 4); }
@@ -160,11 +160,11 @@ static __global__ void embed_kernel(DevMat e, const int32_t *__restrict__ tokens
         if (e.type == NL_Q4_0) {
             int64_t blk = idx >> 5; int el = (int)(idx & 31);
             uint8_t byte = e.qs[blk * 16 + (el & 15)];
-            v = (float)((int)(el < 16 ? (byte & 0x0F) : (byte >> 4)) - 8) * __half2float(e.d[blk]);
+            v = (float)((int)(el < 16 ? (byte & 0x0F) : (byte >> 4)) - 8) * h2f_exact(e.d[blk]);
         } else if (e.type == NL_Q8_0) {
-            v = (float)(int8_t)e.qs[idx] * __half2float(e.d[idx >> 5]);
+            v = (float)(int8_t)e.qs[idx] * h2f_exact(e.d[idx >> 5]);
         } else if (e.type == NL_F16) {
-            v = __half2float(reinterpret_cast<const __half *>(e.qs)[idx]);
+            v = h2f_exact(reinterpret_cast<const __half *>(e.qs)[idx]);
         } else if (e.type == NL_F32) {
             v = reinterpret_cast<const float *>(e.qs)[idx];
         } else {
