@@ -7,8 +7,12 @@
 
 #include <vector>
 
+#include <stdlib.h>
+
 #include "nl_gemv.cuh"
 #include "nl_kernels.cuh"
+#include "nl_stream.cuh"
+#include "nl_mega.cuh"
 
 namespace nl {
 
@@ -126,6 +130,72 @@ __global__ void swiglu_kernel(float *__restrict__ hb, const float *__restrict__ 
     if (i < n) hb[i] = silu_f(hb[i]) * hb2[i];
 }
 
+
+struct GemvOpts { int num_sms; bool stream; bool pdl; };
+static GemvOpts default_opts(int device) {
+    GemvOpts o{148, true, true};
+    cudaDeviceGetAttribute(&o.num_sms, cudaDevAttrMultiProcessorCount, device);
+    if (getenv("NL_NO_STREAM")) o.stream = false;   // A/B switch: fall back to the simple per-row-tile GEMV
+    if (getenv("NL_NO_PDL")) o.pdl = false;
+    return o;
+}
+
+// One (possibly multi-segment) matmulDispatch.  norm_w != nullptr asks for out = W · RMSNorm(x; norm_w) (go/quant.go:597-607):
+// fused into the streaming kernel's prologue when it applies, otherwise done by rmsnorm_kernel into `scratch`.
+// Returns the number of kernel launches issued through *launches.
+static int gemv_dispatch(const MatRef *mats, int nmat, const float *x, int x_stride, int batch, int epi, const float *norm_w, float eps,
+                         float *scratch, const GemvOpts &o, cudaStream_t st, int *launches) {
+    const DevMat &w0 = *mats[0].w;
+    const int type = w0.type, cols = (int)w0.cols;
+    const int NM = epi == EPI_SWIGLU ? 2 : 1;
+    bool same = true;
+    for (int i = 0; i < nmat; i++) same = same && mats[i].w->type == type && mats[i].w->cols == w0.cols && (NM == 1 || (mats[i].w2->type == type && mats[i].w2->cols == w0.cols));
+    if (o.stream && batch == 1 && same) {
+        int rows[3];
+        for (int i = 0; i < nmat; i++) rows[i] = (int)mats[i].w->rows;
+        StreamPlan p = plan_stream(type, rows, nmat, cols, NM, o.num_sms);
+        if (p.ok) {
+            StreamArgs a; memset(&a, 0, sizeof a);
+            a.nseg = nmat; a.x = x; a.norm_w = norm_w; a.eps = eps; a.cols = cols; a.nb = p.nb; a.nb_pad = p.nb_pad; a.RG = p.RG; a.T = p.T;
+            a.stages = p.stages; a.stage_bytes = p.stage_bytes; a.epi = epi == EPI_RESID ? SEPI_RESID : epi == EPI_SWIGLU ? SEPI_SWIGLU : SEPI_STORE;
+            int tiles = 0;
+            for (int i = 0; i < nmat; i++) {
+                const DevMat &w = *mats[i].w;
+                a.seg[i].qs = w.qs; a.seg[i].d = w.d;
+                if (NM == 2) { a.seg[i].qs2 = mats[i].w2->qs; a.seg[i].d2 = mats[i].w2->d; }
+                a.seg[i].bias = mats[i].bias; a.seg[i].out = mats[i].out; a.seg[i].rows = rows[i]; a.seg[i].tile_begin = tiles;
+                tiles += (rows[i] + p.T - 1) / p.T;
+            }
+            a.total_tiles = tiles;
+            const int act = norm_w ? ACT_RMSNORM : ACT_NONE;
+            int rc = type == NL_Q4_0 ? launch_stream_q4_0(a, NM, p.RPT, act, p.grid, p.smem, st, o.pdl)
+                   : type == NL_Q8_0 ? launch_stream_q8_0(a, NM, p.RPT, act, p.grid, p.smem, st, o.pdl)
+                                     : launch_stream_f16(a, NM, p.RPT, act, p.grid, p.smem, st, o.pdl);
+            if (rc) return fail(NL_ERR_CUDA, "stream gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+            if (launches) (*launches)++;
+            return NL_OK;
+        }
+    }
+    // ---- fallback path ----
+    const float *xin = x;
+    if (norm_w) {
+        const int nt = cols >= 4096 ? 1024 : cols >= 1024 ? 512 : 256;
+        rmsnorm_kernel<<<batch, nt, 0, st>>>(x, norm_w, scratch, cols, eps);
+        if (launches) (*launches)++;
+        xin = scratch;
+    }
+    const bool simple_ok = type == NL_Q4_0 || type == NL_Q8_0 || type == NL_F16 || type == NL_F32;
+    if (same && (simple_ok || epi != EPI_SWIGLU)) {
+        if (simple_ok) { int rc = gemv_multi(mats, nmat, xin, x_stride, batch, epi, st); if (rc) return rc; if (launches) (*launches)++; }
+        else for (int i = 0; i < nmat; i++) { int rc = gemv_multi(&mats[i], 1, xin, x_stride, batch, epi, st); if (rc) return rc; if (launches) (*launches)++; }
+        return NL_OK;
+    }
+    // mixed types (or SwiGLU over raw-block types): one launch per matrix, SwiGLU as a separate pass
+    if (epi == EPI_SWIGLU) return fail(NL_ERR_STATE, "internal: unfused swiglu must be issued by the caller");
+    for (int i = 0; i < nmat; i++) { int rc = gemv_multi(&mats[i], 1, xin, x_stride, batch, epi, st); if (rc) return rc; if (launches) (*launches)++; }
+    return NL_OK;
+}
+
 }  // namespace nl
 
 using namespace nl;
@@ -157,6 +227,12 @@ struct nl_model {
     int launches_fwd = 0;
     int64_t weight_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
+    GemvOpts opts{148, true, true};
+    // per-token persistent kernel (batch 1)
+    bool mega_ok = false;
+    MegaPhase *d_phases = nullptr; unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;
+    MegaArgs margs; int mega_grid = 0; size_t mega_smem = 0; int mega_type = -1;
+    unsigned long long *d_trace = nullptr;
 };
 
 static int set_dev(const nl_model *m) {
@@ -178,6 +254,101 @@ static int upload_vec(float **dst, int type, int64_t n, const void *host, size_t
     return rc;
 }
 
+// Plan one GEMV phase of the persistent kernel; returns false when the shape cannot be tiled for it.
+static bool plan_mega_gemv(MegaPhase &P, int type, const MatRef *mats, int nmat, int NM, int epi, int xsrc, const float *x, const float *norm_w) {
+    const DevMat &w0 = *mats[0].w;
+    const int QB = type == NL_Q4_0 ? 16 : type == NL_Q8_0 ? 32 : 64, DB = type == NL_F16 ? 0 : 2;
+    memset(&P, 0, sizeof P);
+    P.kind = PH_GEMV; P.nseg = nmat; P.x = x; P.norm_w = norm_w; P.xsrc = xsrc; P.epi = epi; P.NM = NM;
+    P.cols = (int)w0.cols; P.nb = P.cols / 32; P.nb_pad = (P.nb + 31) / 32 * 32;
+    if (P.cols % 32 || P.nb_pad > MG_CONSUMERS) return false;
+    P.RG = MG_CONSUMERS / P.nb_pad;
+    if (DB && ((P.RG * P.nb * DB) % 16)) return false;            // every chunk's scale-plane slice must be a 16-byte multiple
+    P.upc = 4 / NM;
+    while (P.upc > 1 && NM * P.upc * P.RG * P.nb * (QB + DB) > 56 * 1024) P.upc >>= 1;
+    P.upc_log2 = P.upc == 4 ? 2 : P.upc == 2 ? 1 : 0;
+    P.q_chunk_bytes = P.upc * P.RG * P.nb * QB; P.d_chunk_bytes = P.upc * P.RG * P.nb * DB;
+    if (NM * (P.q_chunk_bytes + P.d_chunk_bytes) > 56 * 1024) return false;
+    int units = 0;
+    for (int i = 0; i < nmat; i++) {
+        const DevMat &w = *mats[i].w;
+        if (w.type != type || w.cols != w0.cols) return false;
+        if (NM == 2 && (mats[i].w2->type != type || mats[i].w2->cols != w0.cols || mats[i].w2->rows != w.rows)) return false;
+        if (DB && ((w.rows * P.nb * DB) % 16)) return false;
+        P.seg[i].qs = w.qs; P.seg[i].d = w.d;
+        if (NM == 2) { P.seg[i].qs2 = mats[i].w2->qs; P.seg[i].d2 = mats[i].w2->d; }
+        P.seg[i].bias = mats[i].bias; P.seg[i].out = mats[i].out; P.seg[i].rows = (int)w.rows; P.seg[i].tile_begin = units;
+        P.seg_units[i] = (int)((w.rows + P.RG - 1) / P.RG);
+        units += P.seg_units[i];
+    }
+    P.total_units = units;
+    return true;
+}
+
+// Build the phase list of the per-token persistent kernel (see nl_mega.cuh).  Leaves mega_ok=false when the model does not fit
+// its constraints (mixed tensor types, raw-block types, head_dim != 64, GQA group > 8, ...): the multi-kernel path is used then.
+static int build_mega(nl_model *m) {
+    const nl_config &c = m->c;
+    m->mega_ok = false;
+    if (getenv("NL_NO_MEGA")) return NL_OK;
+    const int type = m->L[0].wq.type;
+    if (type != NL_Q4_0 && type != NL_Q8_0 && type != NL_F16) return NL_OK;
+    if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
+    const int G = m->opts.num_sms;
+    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size;
+    std::vector<MegaPhase> ph;
+    MegaPhase P;
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        MatRef qkv[3] = {{&ly.wq, nullptr, ly.bq, m->q, qdim}, {&ly.wk, nullptr, ly.bk, m->k, kvd}, {&ly.wv, nullptr, ly.bv, m->v, kvd}};
+        if (!plan_mega_gemv(P, type, qkv, 3, 1, SEPI_STORE, XS_RMSNORM, m->x, ly.attn_norm))  return NL_OK;
+        ph.push_back(P);
+        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
+        MatRef o = {&ly.wo, nullptr, ly.bo, m->x, dim};
+        if (!plan_mega_gemv(P, type, &o, 1, 1, SEPI_RESID, XS_ATTN, nullptr, nullptr))  return NL_OK;
+        ph.push_back(P);
+        MatRef gu = {&ly.wgate, &ly.wup, nullptr, m->hb, ffn};
+        if (!plan_mega_gemv(P, type, &gu, 1, 2, SEPI_SWIGLU, XS_RMSNORM, m->x, ly.ffn_norm))  return NL_OK;
+        ph.push_back(P);
+        MatRef dn = {&ly.wdown, nullptr, nullptr, m->x, dim};
+        if (!plan_mega_gemv(P, type, &dn, 1, 1, SEPI_RESID, XS_PLAIN, m->hb, nullptr))  return NL_OK;
+        ph.push_back(P);
+    }
+    const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
+    MatRef lm = {&outw, nullptr, nullptr, m->logits, c.vocab_size};
+    if (!plan_mega_gemv(P, type, &lm, 1, 1, SEPI_STORE, XS_RMSNORM, m->x, m->output_norm))  return NL_OK;
+    ph.push_back(P);
+    int slot = 0;
+    for (auto &p : ph) if (p.kind == PH_GEMV) { int b = p.NM * (p.q_chunk_bytes + p.d_chunk_bytes); if (b > slot) slot = b; }
+    slot = (slot + 127) / 128 * 128;
+    int stages = (int)((168 * 1024) / slot);  // + ~38 KB static smem of the kernel, under the 227 KB per-CTA limit
+    if (stages > MG_MAX_STAGES) stages = MG_MAX_STAGES;
+    if (stages < 2) return NL_OK;
+    int nsplit = G / c.n_kv_heads;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
+    NL_CUDA(cudaMalloc(&m->d_phases, ph.size() * sizeof(MegaPhase)));
+    NL_CUDA(cudaMemcpy(m->d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
+    NL_CUDA(cudaMalloc(&m->d_bar, ph.size() * sizeof(unsigned int)));
+    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 4));
+    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
+    MegaArgs &a = m->margs;
+    memset(&a, 0, sizeof a);
+    a.phases = m->d_phases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.stages = stages; a.slot_bytes = slot;
+    a.at.q = m->q; a.at.k = m->k; a.at.v = m->v; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
+    a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
+    a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
+    a.at.nsplit = nsplit; a.at.eps = c.rms_norm_eps; a.at.scale = (float)(1.0 / sqrt((double)m->hd));
+    if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
+        NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
+        a.trace = m->d_trace;
+    }
+    m->mega_grid = G; m->mega_smem = (size_t)stages * slot; m->mega_type = type;
+    m->mega_ok = true;
+    return NL_OK;
+}
+
 // The launch sequence of one Forward for `batch` sequences (go/model.go:490-620).  Recorded into a CUDA graph.
 static int record_forward(nl_model *m, int batch) {
     const nl_config &c = m->c;
@@ -189,17 +360,25 @@ static int record_forward(nl_model *m, int batch) {
         embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim);
         launches++;
     }
-    const int nthreads_norm = dim >= 4096 ? 1024 : dim >= 1024 ? 512 : 256;
+    if (batch == 1 && m->mega_ok) {
+        // everything after the embedding in ONE persistent kernel (nl_mega.cuh); its grid-barrier counters start at zero
+        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, (size_t)m->margs.n_phases * sizeof(unsigned int), st));
+        int rc = m->mega_type == NL_Q4_0 ? launch_mega_q4_0(m->margs, m->mega_grid, m->mega_smem, st)
+               : m->mega_type == NL_Q8_0 ? launch_mega_q8_0(m->margs, m->mega_grid, m->mega_smem, st)
+                                         : launch_mega_f16(m->margs, m->mega_grid, m->mega_smem, st);
+        if (rc) return fail(NL_ERR_CUDA, "persistent decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        launches++;
+        NL_CUDA(cudaGetLastError());
+        m->launches_fwd = launches;
+        return NL_OK;
+    }
+    const GemvOpts &o = m->opts;
+    const float eps = c.rms_norm_eps;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
-        rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, ly.attn_norm, m->xb, dim, c.rms_norm_eps); launches++;
-        {   // Q, K, V projections (+bias), model.go:520-527 — one launch when the three share a type
+        {   // attention pre-norm + Q, K, V projections (+bias), model.go:517-527 — one launch when the three share a type
             MatRef r[3] = {{&ly.wq, nullptr, ly.bq, m->q, qdim}, {&ly.wk, nullptr, ly.bk, m->k, kvd}, {&ly.wv, nullptr, ly.bv, m->v, kvd}};
-            if (ly.wq.type == ly.wk.type && ly.wq.type == ly.wv.type && type_supported(ly.wq.type) && blk_elems(ly.wq.type) <= 32) {
-                int rc = gemv_multi(r, 3, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++;
-            } else {
-                for (int i = 0; i < 3; i++) { int rc = gemv_multi(&r[i], 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++; }
-            }
+            int rc = gemv_dispatch(r, 3, m->x, dim, batch, EPI_STORE, ly.attn_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
         }
         {   // RoPE, QK-norm, KV write, attention: model.go:530-587
             AttnArgs a;
@@ -216,33 +395,32 @@ static int record_forward(nl_model *m, int batch) {
         }
         {   // output projection + residual, model.go:590-594
             MatRef r = {&ly.wo, nullptr, ly.bo, m->x, dim};
-            int rc = gemv_multi(&r, 1, m->xb2, qdim, batch, EPI_RESID, st); if (rc) return rc; launches++;
+            int rc = gemv_dispatch(&r, 1, m->xb2, qdim, batch, EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
         }
-        rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, ly.ffn_norm, m->xb, dim, c.rms_norm_eps); launches++;
-        {   // gate/up + SiLU*up, model.go:600-606
-            bool fused = ly.wgate.type == ly.wup.type && (ly.wgate.type == NL_Q4_0 || ly.wgate.type == NL_Q8_0 || ly.wgate.type == NL_F16 || ly.wgate.type == NL_F32);
-            if (fused) {
+        {   // FFN pre-norm + gate/up + SiLU*up, model.go:597-606
+            const int gt = ly.wgate.type;
+            bool fusable = gt == ly.wup.type && (gt == NL_Q4_0 || gt == NL_Q8_0 || gt == NL_F16 || gt == NL_F32);
+            if (fusable) {
                 MatRef r = {&ly.wgate, &ly.wup, nullptr, m->hb, ffn};
-                int rc = gemv_multi(&r, 1, m->xb, dim, batch, EPI_SWIGLU, st); if (rc) return rc; launches++;
+                int rc = gemv_dispatch(&r, 1, m->x, dim, batch, EPI_SWIGLU, ly.ffn_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
             } else {
                 MatRef g = {&ly.wgate, nullptr, nullptr, m->hb, ffn}, u = {&ly.wup, nullptr, nullptr, m->hb2, ffn};
-                int rc = gemv_multi(&g, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc;
-                rc = gemv_multi(&u, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc;
+                int rc = gemv_dispatch(&g, 1, m->x, dim, batch, EPI_STORE, ly.ffn_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
+                rc = gemv_dispatch(&u, 1, m->xb, dim, batch, EPI_STORE, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;  // xb holds the normed input
                 int64_t n = (int64_t)batch * ffn;
                 swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->hb, m->hb2, n);
-                launches += 3;
+                launches++;
             }
         }
         {   // down projection + residual, model.go:609-612
             MatRef r = {&ly.wdown, nullptr, nullptr, m->x, dim};
-            int rc = gemv_multi(&r, 1, m->hb, ffn, batch, EPI_RESID, st); if (rc) return rc; launches++;
+            int rc = gemv_dispatch(&r, 1, m->hb, ffn, batch, EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
         }
     }
-    rmsnorm_kernel<<<batch, nthreads_norm, 0, st>>>(m->x, m->output_norm, m->xb, dim, c.rms_norm_eps); launches++;  // model.go:616
-    {   // LM head, model.go:619
+    {   // final norm + LM head, model.go:616-619
         const DevMat &out = m->output.present() ? m->output : m->tok_embd;
         MatRef r = {&out, nullptr, nullptr, m->logits, c.vocab_size};
-        int rc = gemv_multi(&r, 1, m->xb, dim, batch, EPI_STORE, st); if (rc) return rc; launches++;
+        int rc = gemv_dispatch(&r, 1, m->x, dim, batch, EPI_STORE, m->output_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
     }
     NL_CUDA(cudaGetLastError());
     m->launches_fwd = launches;
@@ -330,6 +508,7 @@ int nl_create(const nl_config *cfg, nl_model **out) {
     nl_model *m = new nl_model();
     m->c = c; m->dim = c.embed_dim; m->hd = c.head_dim; m->kvd = c.n_kv_heads * c.head_dim; m->qdim = c.n_heads * c.head_dim; m->B = c.max_batch;
     m->L.resize(c.n_layers);
+    m->opts = default_opts(c.device);
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
     if (e != cudaSuccess) { delete m; return fail(NL_ERR_CUDA, "cudaStreamCreate: %s", cudaGetErrorString(e)); }
     *out = m;
@@ -442,6 +621,8 @@ int nl_finalize(nl_model *m) {
     for (auto &ly : m->L) wb += ly.wq.bytes() + ly.wk.bytes() + ly.wv.bytes() + ly.wo.bytes() + ly.wgate.bytes() + ly.wup.bytes() + ly.wdown.bytes() + 2 * (int64_t)dim * 4;
     m->weight_bytes = wb;
     if (S * sizeof(float) > 48 * 1024) return fail(NL_ERR_INVALID, "seq_len too large for the attention kernel");
+    rc = build_mega(m);
+    if (rc) return rc;
     rc = build_graphs(m, 1);
     if (rc) return rc;
     m->finalized = true;
@@ -463,6 +644,11 @@ void nl_destroy(nl_model *m) {
     for (float *p : fs) if (p) cudaFree(p);
     int32_t *is[] = {m->gamma_map, m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->d_prompt, m->d_cursor};
     for (int32_t *p : is) if (p) cudaFree(p);
+    if (m->d_trace) cudaFree(m->d_trace);
+    if (m->d_phases) cudaFree(m->d_phases);
+    if (m->d_bar) cudaFree(m->d_bar);
+    if (m->part_acc) cudaFree(m->part_acc);
+    if (m->part_ml) cudaFree(m->part_ml);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_logits) cudaFreeHost(m->h_logits);
     if (m->ev0) cudaEventDestroy(m->ev0);
@@ -598,6 +784,13 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
     NL_CUDA(cudaEventRecord(m->ev1, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));
     NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
+    if (m->d_trace && getenv("NL_TRACE")) {
+        size_t n = (size_t)m->mega_grid * m->margs.n_phases * 8;
+        std::vector<unsigned long long> h(n);
+        NL_CUDA(cudaMemcpy(h.data(), m->d_trace, n * 8, cudaMemcpyDeviceToHost));
+        FILE *f = fopen(getenv("NL_TRACE"), "wb");
+        if (f) { int hdr[2] = {m->mega_grid, m->margs.n_phases}; fwrite(hdr, 4, 2, f); fwrite(h.data(), 8, n, f); fclose(f); }
+    }
     return NL_OK;
 }
 
@@ -638,6 +831,7 @@ struct nl_matrix {
     std::vector<DevMat> copies;  // replicas for L2-cold benchmarking; [0] is the matrix
     float *x = nullptr, *out = nullptr; int xcap = 0;
     cudaStream_t st = nullptr;
+    GemvOpts opts{148, true, true};
 };
 
 int nl_matrix_create(uint32_t type, const void *host_w, int64_t rows, int64_t cols, int32_t device, nl_matrix **out) {
@@ -645,7 +839,7 @@ int nl_matrix_create(uint32_t type, const void *host_w, int64_t rows, int64_t co
     *out = nullptr;
     int rc = check_device(device); if (rc) return rc;
     if (rows > INT32_MAX || cols > INT32_MAX) return fail(NL_ERR_INVALID, "matrix too large");
-    nl_matrix *w = new nl_matrix(); w->device = device; w->copies.resize(1);
+    nl_matrix *w = new nl_matrix(); w->device = device; w->copies.resize(1); w->opts = default_opts(device);
     cudaStreamCreateWithFlags(&w->st, cudaStreamNonBlocking);
     int64_t nb = tensor_nbytes((int)type, rows * cols);
     rc = upload_mat(w->copies[0], (int)type, rows, cols, host_w, nb < 0 ? 0 : (size_t)nb, w->st);
@@ -671,7 +865,7 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
     const DevMat &m = w->copies[0];
     NL_CUDA(cudaMemcpyAsync(w->x, host_x, (size_t)batch * m.cols * 4, cudaMemcpyHostToDevice, w->st));
     MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
-    rc = gemv_multi(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, w->st); if (rc) return rc;
+    rc = gemv_dispatch(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
     NL_CUDA(cudaMemcpyAsync(host_out, w->out, (size_t)batch * m.rows * 4, cudaMemcpyDeviceToHost, w->st));
     NL_CUDA(cudaStreamSynchronize(w->st));
     return NL_OK;
@@ -695,7 +889,7 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     for (int i = 0; i < warmup + iters; i++) {
         if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));
         MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
-        rc = gemv_multi(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, w->st); if (rc) return rc;
+        rc = gemv_dispatch(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
         idx = (idx + 1) % n_copies;
     }
     NL_CUDA(cudaEventRecord(e1, w->st));

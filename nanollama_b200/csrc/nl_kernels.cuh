@@ -226,6 +226,7 @@ static __global__ void __launch_bounds__(128) attn_decode_kernel(const AttnArgs 
     const int pos = a.pos[b];
     extern __shared__ float sc[];  // [seq_len] scores
     __shared__ float sq[HD], sk[HD], sv[HD], red[8], part[2][HD];
+    asm volatile("griddepcontrol.launch_dependents;" ::: "memory");  // let the next (PDL) GEMV start streaming its weights
 
     // --- load + RoPE: threads [0,HALF) rotate q, [HALF,2*HALF) rotate k, next HD threads copy v
     const float *cs = a.cos_t + (int64_t)pos * HALF, *sn = a.sin_t + (int64_t)pos * HALF;
