@@ -233,6 +233,9 @@ struct nl_model {
     MegaPhase *d_phases = nullptr; unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;
     MegaArgs margs; int mega_grid = 0; size_t mega_smem = 0; int mega_type = -1;
     unsigned long long *d_trace = nullptr;
+    int mega_reps = 1;
+    int act_stride = 0;          // floats between the MG_REPS copies of x / xb2 / hb (replica 0 is what every other path uses)
+    float *attn_out = nullptr;   // xb2 with replicas
 };
 
 static int set_dev(const nl_model *m) {
@@ -255,11 +258,13 @@ static int upload_vec(float **dst, int type, int64_t n, const void *host, size_t
 }
 
 // Plan one GEMV phase of the persistent kernel; returns false when the shape cannot be tiled for it.
-static bool plan_mega_gemv(MegaPhase &P, int type, const MatRef *mats, int nmat, int NM, int epi, int xsrc, const float *x, const float *norm_w) {
+static bool plan_mega_gemv(MegaPhase &P, int type, const MatRef *mats, int nmat, int NM, int epi, int xsrc, const float *x, const float *norm_w,
+                           int x_reps, int out_reps, int stride) {
     const DevMat &w0 = *mats[0].w;
     const int QB = type == NL_Q4_0 ? 16 : type == NL_Q8_0 ? 32 : 64, DB = type == NL_F16 ? 0 : 2;
     memset(&P, 0, sizeof P);
     P.kind = PH_GEMV; P.nseg = nmat; P.x = x; P.norm_w = norm_w; P.xsrc = xsrc; P.epi = epi; P.NM = NM;
+    P.x_reps = x_reps; P.x_stride = stride; P.out_reps = out_reps; P.out_stride = stride;
     P.cols = (int)w0.cols; P.nb = P.cols / 32; P.nb_pad = (P.nb + 31) / 32 * 32;
     if (P.cols % 32 || P.nb_pad > MG_CONSUMERS) return false;
     P.RG = MG_CONSUMERS / P.nb_pad;
@@ -290,7 +295,8 @@ static bool plan_mega_gemv(MegaPhase &P, int type, const MatRef *mats, int nmat,
 static int build_mega(nl_model *m) {
     const nl_config &c = m->c;
     m->mega_ok = false;
-    if (getenv("NL_NO_MEGA")) return NL_OK;
+    // Opt-in (NL_MEGA=1): on B200 the persistent kernel currently trails the PDL-chained per-matrix kernels
+    if (!getenv("NL_MEGA") || getenv("NL_NO_MEGA")) return NL_OK;
     const int type = m->L[0].wq.type;
     if (type != NL_Q4_0 && type != NL_Q8_0 && type != NL_F16) return NL_OK;
     if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
@@ -298,25 +304,28 @@ static int build_mega(nl_model *m) {
     const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size;
     std::vector<MegaPhase> ph;
     MegaPhase P;
+    int R = 1; const int S = m->act_stride;
+    if (getenv("NL_REPS")) { R = atoi(getenv("NL_REPS")); if (R < 1) R = 1; if (R > MG_REPS) R = MG_REPS; }
+    m->mega_reps = R;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
         MatRef qkv[3] = {{&ly.wq, nullptr, ly.bq, m->q, qdim}, {&ly.wk, nullptr, ly.bk, m->k, kvd}, {&ly.wv, nullptr, ly.bv, m->v, kvd}};
-        if (!plan_mega_gemv(P, type, qkv, 3, 1, SEPI_STORE, XS_RMSNORM, m->x, ly.attn_norm))  return NL_OK;
+        if (!plan_mega_gemv(P, type, qkv, 3, 1, SEPI_STORE, XS_RMSNORM, m->x, ly.attn_norm, R, 1, S)) return NL_OK;
         ph.push_back(P);
         memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
         MatRef o = {&ly.wo, nullptr, ly.bo, m->x, dim};
-        if (!plan_mega_gemv(P, type, &o, 1, 1, SEPI_RESID, XS_ATTN, nullptr, nullptr))  return NL_OK;
+        if (!plan_mega_gemv(P, type, &o, 1, 1, SEPI_RESID, XS_PLAIN, m->xb2, nullptr, R, R, S)) return NL_OK;
         ph.push_back(P);
         MatRef gu = {&ly.wgate, &ly.wup, nullptr, m->hb, ffn};
-        if (!plan_mega_gemv(P, type, &gu, 1, 2, SEPI_SWIGLU, XS_RMSNORM, m->x, ly.ffn_norm))  return NL_OK;
+        if (!plan_mega_gemv(P, type, &gu, 1, 2, SEPI_SWIGLU, XS_RMSNORM, m->x, ly.ffn_norm, R, R, S)) return NL_OK;
         ph.push_back(P);
         MatRef dn = {&ly.wdown, nullptr, nullptr, m->x, dim};
-        if (!plan_mega_gemv(P, type, &dn, 1, 1, SEPI_RESID, XS_PLAIN, m->hb, nullptr))  return NL_OK;
+        if (!plan_mega_gemv(P, type, &dn, 1, 1, SEPI_RESID, XS_PLAIN, m->hb, nullptr, R, R, S)) return NL_OK;
         ph.push_back(P);
     }
     const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
     MatRef lm = {&outw, nullptr, nullptr, m->logits, c.vocab_size};
-    if (!plan_mega_gemv(P, type, &lm, 1, 1, SEPI_STORE, XS_RMSNORM, m->x, m->output_norm))  return NL_OK;
+    if (!plan_mega_gemv(P, type, &lm, 1, 1, SEPI_STORE, XS_RMSNORM, m->x, m->output_norm, R, 1, S)) return NL_OK;
     ph.push_back(P);
     int slot = 0;
     for (auto &p : ph) if (p.kind == PH_GEMV) { int b = p.NM * (p.q_chunk_bytes + p.d_chunk_bytes); if (b > slot) slot = b; }
@@ -329,16 +338,18 @@ static int build_mega(nl_model *m) {
     if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
     NL_CUDA(cudaMalloc(&m->d_phases, ph.size() * sizeof(MegaPhase)));
     NL_CUDA(cudaMemcpy(m->d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    NL_CUDA(cudaMalloc(&m->d_bar, ph.size() * sizeof(unsigned int)));
+    const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
+    NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
     NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 4));
     NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
     MegaArgs &a = m->margs;
     memset(&a, 0, sizeof a);
+    a.hold_mode = getenv("NL_HOLD") ? atoi(getenv("NL_HOLD")) : 0;
     a.phases = m->d_phases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.stages = stages; a.slot_bytes = slot;
     a.at.q = m->q; a.at.k = m->k; a.at.v = m->v; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
     a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
-    a.at.nsplit = nsplit; a.at.eps = c.rms_norm_eps; a.at.scale = (float)(1.0 / sqrt((double)m->hd));
+    a.at.nsplit = nsplit; a.at.out = m->xb2; a.at.out_reps = R; a.at.out_stride = S; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps; a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
         NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
         NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
@@ -357,12 +368,12 @@ static int record_forward(nl_model *m, int batch) {
     int launches = 0;
     {   // 1. embedding (+gamma), model.go:500-507
         dim3 grid((dim + 255) / 256, batch);
-        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim, (batch == 1 && m->mega_ok) ? m->mega_reps : 1, m->act_stride);
         launches++;
     }
     if (batch == 1 && m->mega_ok) {
         // everything after the embedding in ONE persistent kernel (nl_mega.cuh); its grid-barrier counters start at zero
-        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, (size_t)m->margs.n_phases * sizeof(unsigned int), st));
+        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->margs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
         int rc = m->mega_type == NL_Q4_0 ? launch_mega_q4_0(m->margs, m->mega_grid, m->mega_smem, st)
                : m->mega_type == NL_Q8_0 ? launch_mega_q8_0(m->margs, m->mega_grid, m->mega_smem, st)
                                          : launch_mega_f16(m->margs, m->mega_grid, m->mega_smem, st);
@@ -592,8 +603,14 @@ int nl_finalize(nl_model *m) {
     }
     const int B = m->B, dim = m->dim, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, half = m->hd / 2;
     auto alloc = [&](float **p, size_t n) -> int { NL_CUDA(cudaMalloc(p, n * 4)); NL_CUDA(cudaMemset(*p, 0, n * 4)); return NL_OK; };
-    if ((rc = alloc(&m->x, (size_t)B * dim)) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, (size_t)B * qdim)) ||
-        (rc = alloc(&m->hb, (size_t)B * c.interm_size)) || (rc = alloc(&m->hb2, (size_t)B * c.interm_size)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
+    {   // x, xb2 and hb double as the replicated activation vectors of the persistent batch-1 kernel
+        int mx = dim > qdim ? dim : qdim; if (c.interm_size > mx) mx = c.interm_size;
+        m->act_stride = (mx + 31) / 32 * 32;
+    }
+    const size_t rep_floats = (size_t)MG_REPS * m->act_stride;
+    auto mx2 = [](size_t a, size_t b) { return a > b ? a : b; };
+    if ((rc = alloc(&m->x, mx2((size_t)B * dim, rep_floats))) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, mx2((size_t)B * qdim, rep_floats))) ||
+        (rc = alloc(&m->hb, mx2((size_t)B * c.interm_size, rep_floats))) || (rc = alloc(&m->hb2, (size_t)B * c.interm_size)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
         (rc = alloc(&m->k, (size_t)B * kvd)) || (rc = alloc(&m->v, (size_t)B * kvd)) || (rc = alloc(&m->logits, (size_t)B * c.vocab_size)) ||
         (rc = alloc(&m->kc, (size_t)B * c.n_layers * S * kvd)) || (rc = alloc(&m->vc, (size_t)B * c.n_layers * S * kvd)))
         return rc;

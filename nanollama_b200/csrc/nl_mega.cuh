@@ -23,6 +23,10 @@ constexpr int MG_MAX_STAGES = 8;
 constexpr int MG_RED = 96;                            // 4 partials per thread and chunk x (RG * warps-per-row <= 24)
 constexpr int MG_MAX_GROUP = 8;                       // q heads per kv head handled by one attention item
 constexpr int MG_MAX_SPLIT = 16;
+constexpr int MG_REPS = 8;                            // activation vectors are kept in this many copies so that 148 CTAs do not
+                                                      // all queue on the same L2 lines when a phase starts
+constexpr bool MG_GATE_PREFETCH = false;               // true: request a phase's weights only after its input loads were issued
+                                                      // (measured slower on B200: the ring should run ahead across phase boundaries)
 constexpr int MG_XS_FLOATS = 4096;                     // phase inputs up to this length are shared between row groups via smem
 constexpr int MG_ATT_CHUNK = 256;                     // max positions per attention item pass buffer
 
@@ -39,7 +43,9 @@ struct MegaPhase {
     int nseg, total_units;
     int seg_units[3];     // units per segment (ceil(rows / RG)), so the device never divides
     int upc_log2;
-    const float *x;       // XS_PLAIN / XS_RMSNORM input vector [cols]
+    const float *x;       // XS_PLAIN / XS_RMSNORM input vector [cols] (replica 0)
+    int x_reps, x_stride; // copies of x (CTA b reads copy b % x_reps) and floats between copies
+    int out_reps, out_stride;  // copies of the output vector the finisher writes (same for every segment)
     const float *norm_w;  // XS_RMSNORM
     int xsrc, epi, NM;
     int upc;              // units per chunk and matrix (NM * upc <= 4), sized so that a chunk stays <= ~56 KB
@@ -56,6 +62,9 @@ struct MegaAttn {
     const int32_t *pos;          // device scalar
     float *part_acc;             // [H][nsplit][hd]   un-normalised partial outputs
     float *part_ml;              // [H][nsplit][2]    (running max, sum of exp)
+    float *out;                  // [reps][H*hd] combined attention output (written by the last split of each kv head)
+    int out_reps, out_stride;
+    unsigned int *split_cnt;     // [L][n_kv_heads] arrival counters of the splits, zeroed with the phase barriers
     int n_heads, n_kv_heads, seq_len, qk_norm, conj, nsplit;
     float eps, scale;
 };
@@ -67,6 +76,7 @@ struct MegaArgs {
     MegaAttn at;
     float eps;
     int stages, slot_bytes;
+    int hold_mode;               // 0: ring refill never waits; 1: not between 'phase consumed' and 'next input in registers'; 2: gate per phase
     unsigned long long *trace;   // optional (NL_TRACE): [cta][phase][8] globaltimer stamps for latency forensics
 };
 
@@ -160,6 +170,11 @@ __device__ __forceinline__ void phase_arrive(unsigned int *bar, int p) {
 __device__ __forceinline__ void phase_wait(const unsigned int *bar, int p, unsigned int G) {
     while (ld_acquire(bar + p) < G) { __nanosleep(20); }
 }
+__device__ __forceinline__ bool mbar_test(uint64_t *bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile("{\n\t.reg .pred p;\n\tmbarrier.test_wait.parity.shared::cta.b64 p, [%1], %2;\n\tselp.u32 %0, 1, 0, p;\n\t}" : "=r"(ok) : "r"(smem_u32(bar)), "r"(parity) : "memory");
+    return ok != 0;
+}
 // chunk enumeration shared by the producer and the math warps: next chunk of the CTA's unit range [u, u_end)
 struct Chunk { int seg, row0, nunits, rows; };
 __device__ __forceinline__ Chunk next_chunk(const MegaPhase &P, int &u, int u_end) {
@@ -192,7 +207,7 @@ __device__ __forceinline__ void tile_band(int total, int b, int G, int &t0, int 
 // consumer side of one GEMV phase
 template <int TYPE, int NM>
 __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase &P, uint8_t *smem, uint64_t *full_bar, uint64_t *empty_bar,
-                                              float (*red)[MG_RED], double *ss_red, float *inv_s, float *xs, int &it, int warp, int lane) {
+                                              float (*red)[MG_RED], double *ss_red, float *inv_s, float *xs, int *hold, int *hold1, int &it, int warp, int lane, int p) {
     constexpr int QB = BlkBytes<TYPE>::Q, DB = BlkBytes<TYPE>::D;
     const int UPC = P.upc;       // units per chunk and matrix; NM * UPC <= 4 partials per thread and chunk
     const int nb = P.nb, wpr = P.nb_pad >> 5;
@@ -239,20 +254,21 @@ __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase
         }
     } else {
         if (loader) {
-            const float4 *xp = reinterpret_cast<const float4 *>(P.x + c * 32);
+            const float4 *xp = reinterpret_cast<const float4 *>(P.x + (size_t)(blockIdx.x % P.x_reps) * P.x_stride + c * 32);
 #pragma unroll
             for (int i = 0; i < 8; i++) { const float4 v = xp[i]; xr[4 * i] = v.x; xr[4 * i + 1] = v.y; xr[4 * i + 2] = v.z; xr[4 * i + 3] = v.w; }
         } else {
 #pragma unroll
             for (int i = 0; i < 32; i++) xr[i] = 0.f;
         }
-        if (P.xsrc == XS_RMSNORM) {  // RMSNormInto, go/quant.go:597-607: float64 sum of squares, fp32 x*inv*w
-            float4 w4[8];
-            if (loader) {            // norm weights are requested together with x: one L2 round trip, not two
-                const float4 *wp = reinterpret_cast<const float4 *>(P.norm_w + c * 32);
+        float4 w4[8];
+        if (P.xsrc == XS_RMSNORM && loader) {   // norm weights are requested together with x: one L2 round trip, not two
+            const float4 *wp = reinterpret_cast<const float4 *>(P.norm_w + c * 32);
 #pragma unroll
-                for (int i = 0; i < 8; i++) w4[i] = wp[i];
-            }
+            for (int i = 0; i < 8; i++) w4[i] = wp[i];
+        }
+        if (threadIdx.x == 0) *(volatile int *)hold = p;   // input loads are on the wire: the producer may request this phase's weights
+        if (P.xsrc == XS_RMSNORM) {  // RMSNormInto, go/quant.go:597-607: float64 sum of squares, fp32 x*inv*w
             // 32 squares per thread in four fp32 chains, everything across threads in float64 (the reference sums in float64;
             // the difference is far below one fp32 ulp of the resulting scale)
             float q0 = 0.f, q1 = 0.f, q2 = 0.f, q3 = 0.f;
@@ -264,6 +280,7 @@ __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase
                 }
             }
             double ss = ((double)q0 + (double)q1) + ((double)q2 + (double)q3);
+            if (threadIdx.x == 0 && ss >= 0.0) MG_TRACE(p, 6);   // x has landed
             ss = warp_sum_d(ss);
             if (lane == 0) ss_red[warp] = ss;
             mega_consumer_bar();
@@ -273,6 +290,7 @@ __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase
                 if (lane == 0) *inv_s = (float)(1.0 / sqrt(v / (double)P.cols + (double)A.eps));
             }
             mega_consumer_bar();
+            if (threadIdx.x == 0) MG_TRACE(p, 7);                // scale known
             const float inv = *inv_s;
             if (loader) {
 #pragma unroll
@@ -307,7 +325,7 @@ __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase
 #pragma unroll
     for (int i = 0; i < 16; i++) x2[i] = pack2(xr[2 * i], xr[2 * i + 1]);
 
-    if (threadIdx.x == 0) MG_TRACE((int)(&P - A.phases), 2);
+    if (threadIdx.x == 0) { MG_TRACE(p, 2); *(volatile int *)hold1 = 0; }
     // ---- stream the chunks ----
     // everything the inner loop needs lives in registers (the phase descriptor is in global memory)
     const int NS = A.stages, RG = P.RG, lg = P.upc_log2, n_part = NM << lg;
@@ -325,7 +343,7 @@ __device__ __forceinline__ void consume_phase(const MegaArgs &A, const MegaPhase
         float part[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
         for (int pp = 0; pp < 2; pp++) {
-            if (2 * pp < n_part) {  // uniform over the CTA; the two blocks below are straight-line so they interleave
+            if (2 * pp < n_part && ((2 * pp) & ((1 << lg) - 1)) < ch.nunits) {  // uniform over the CTA; the two blocks below are straight-line
 #pragma unroll
                 for (int k = 0; k < 2; k++) {
                     const int pi = 2 * pp + k;
@@ -357,6 +375,7 @@ struct AttnSmem {
     float red[MG_CONSUMER_WARPS][MG_MAX_GROUP];
     float pv[3][MG_MAX_GROUP][64];
     float m_run[MG_MAX_GROUP], l_run[MG_MAX_GROUP], m_new[MG_MAX_GROUP], corr[MG_MAX_GROUP];
+    int is_last;
 };
 
 __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int item, AttnSmem &S, int tid) {
@@ -477,6 +496,32 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
             at.part_ml[(h * at.nsplit + sp) * 2 + 1] = S.l_run[my_h];
         }
     }
+    // The split that arrives last on this kv head folds all splits (fixed order => deterministic) and publishes the final
+    // attention output, so the O-projection reads one plain vector instead of every CTA re-reading all partials.
+    __threadfence();
+    mega_consumer_bar();
+    if (tid == 0) {
+        unsigned int old;
+        asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(at.split_cnt + layer * at.n_kv_heads + kvh) : "memory");
+        S.is_last = (old == (unsigned)at.nsplit - 1u);
+    }
+    mega_consumer_bar();
+    if (S.is_last && tid < threads_per_part) {
+        const int h = kvh * group + my_h;
+        float M = -INFINITY;
+        for (int s = 0; s < at.nsplit; s++) M = fmaxf(M, __ldcg(at.part_ml + (h * at.nsplit + s) * 2));
+        float den = 0.f, o = 0.f;
+        for (int s = 0; s < at.nsplit; s++) {
+            const float m = __ldcg(at.part_ml + (h * at.nsplit + s) * 2), l = __ldcg(at.part_ml + (h * at.nsplit + s) * 2 + 1);
+            if (l > 0.f) {
+                const float wgt = expf(m - M);
+                den = fmaf(wgt, l, den);
+                o = fmaf(wgt, __ldcg(at.part_acc + ((size_t)(h * at.nsplit + s)) * HD + my_d), o);
+            }
+        }
+        o *= 1.0f / den;
+        for (int r = 0; r < at.out_reps; r++) at.out[(size_t)r * at.out_stride + h * HD + my_d] = o;
+    }
     mega_consumer_bar();  // S is reused by the next item of this CTA
 }
 
@@ -489,13 +534,19 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     __shared__ float red[MG_MAX_STAGES][MG_RED];
     __shared__ double ss_red[MG_CONSUMER_WARPS];
     __shared__ float inv_s;
-    __shared__ int pend_phase[MG_MAX_STAGES], pend_seg[MG_MAX_STAGES], pend_row0[MG_MAX_STAGES], pend_rows[MG_MAX_STAGES], pend_last[MG_MAX_STAGES];
+    struct Pend { float *out; const float *bias; int phase, row0, rows, last, RG, wpr, upc, NM, epi, reps, stride; };
+    __shared__ Pend pend[MG_MAX_STAGES];
     __shared__ AttnSmem att;
     __shared__ __align__(16) float xs_buf[MG_XS_FLOATS];
+    __shared__ __align__(16) MegaPhase sph[2];
+    __shared__ int hold1_flag;
+    __shared__ int hold_flag;   // index of the newest phase whose input loads the math warps have issued (-1 at start)
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int NS = A.stages, G = gridDim.x;
     if (tid == 0) {
+        hold1_flag = 0;
+        hold_flag = 0;   // phase 0 may stream right away (its input was produced by the previous kernel)
         for (int s = 0; s < NS; s++) { mbar_init(&full_bar[s], 1); mbar_init(&empty_bar[s], MG_CONSUMER_WARPS); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -503,50 +554,68 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
 
     if (warp == MG_CONSUMER_WARPS) {
         // ===================== producer + finisher warp =====================
+        int *hold = &hold_flag;
         uint64_t policy;  // weights are read once per token: do not let them push activations / KV / norm weights out of L2
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        int it = 0;
-        auto finish = [&](int slot) {   // epilogue of the chunk that occupied `slot`; all 32 lanes
-            const int p = pend_phase[slot];
-            const MegaPhase &P = A.phases[p];
-            const StreamSeg &sg = P.seg[pend_seg[slot]];
-            const int row0 = pend_row0[slot], rows = pend_rows[slot], wpr = P.nb_pad >> 5, upc = P.upc;
-            for (int rr = lane; rr < rows; rr += 32) {
-                const int r = rr / P.RG, rgi = rr % P.RG, row = row0 + rr;
+        auto finish = [&](int slot) {   // epilogue of the chunk that occupied `slot`; all 32 lanes; everything it needs is in smem
+            const Pend q = pend[slot];
+            for (int rr = lane; rr < q.rows; rr += 32) {
+                const int r = rr / q.RG, rgi = rr - r * q.RG, row = q.row0 + rr;
                 float v = 0.f, v2 = 0.f;
-                for (int wi = 0; wi < wpr; wi++) {
-                    v += red[slot][r * 24 + rgi * wpr + wi];
-                    if (P.NM == 2) v2 += red[slot][(upc + r) * 24 + rgi * wpr + wi];
+                for (int wi = 0; wi < q.wpr; wi++) {
+                    v += red[slot][r * 24 + rgi * q.wpr + wi];
+                    if (q.NM == 2) v2 += red[slot][(q.upc + r) * 24 + rgi * q.wpr + wi];
                 }
-                if (sg.bias) v += sg.bias[row];
-                if (P.NM == 2) sg.out[row] = silu_f(v) * v2;       // SiLU(gate)*up, go/model.go:604-606
-                else if (P.epi == SEPI_RESID) sg.out[row] += v;    // X += W·x, go/model.go:592-594, :610-612
-                else sg.out[row] = v;
+                if (q.bias) v += q.bias[row];
+                if (q.NM == 2) v = silu_f(v) * v2;                 // SiLU(gate)*up, go/model.go:604-606
+                else if (q.epi == SEPI_RESID) v += __ldcg(q.out + row);     // X += W·x, go/model.go:592-594, :610-612
+                for (int rep = 0; rep < q.reps; rep++) q.out[(size_t)rep * q.stride + row] = v;
             }
             __syncwarp();
-            if (pend_last[slot] && lane == 0) { MG_TRACE(p, 5); phase_arrive(A.bar, p); MG_TRACE(p, 4); }  // release: cumulative over the warp's stores
+            if (q.last && lane == 0) { MG_TRACE(q.phase, 5); phase_arrive(A.bar, q.phase); MG_TRACE(q.phase, 4); }  // release: cumulative over the warp
             __syncwarp();
         };
-        for (int p = 0; p < A.n_phases; p++) {
-            const MegaPhase &P = A.phases[p];
-            if (P.kind != PH_GEMV) continue;
-            int u, u_end;
-            tile_band(P.total_units, blockIdx.x, G, u, u_end);
-            if (u == u_end) {  // nothing of this phase lands on this CTA: arrive right away
-                if (lane == 0) phase_arrive(A.bar, p);
-                continue;
+        // Issue and finish are decoupled: chunks are issued in program order whenever a ring slot is free and the math warps are
+        // not in a phase prologue (a demand load issued while tens of KB of bulk data are inbound to this SM queues behind them
+        // for microseconds, so the ring is not refilled between "phase p consumed" and "input of phase p+1 in registers");
+        // consumed chunks are finished in order as soon as their empty-barrier completes.
+        int issued = 0, finished = 0;
+        int p = 0, u = 0, u_end = 0;
+        bool have_phase = false, all_issued = false;
+        while (!all_issued || finished < issued) {
+            bool progress = false;
+            if (finished < issued) {
+                const int slot = finished % NS;
+                int done = (lane == 0) ? (int)mbar_test(&empty_bar[slot], (finished / NS) & 1) : 0;
+                done = __shfl_sync(0xffffffffu, done, 0);      // warp-uniform decision
+                if (done) { finish(slot); finished++; progress = true; }
             }
-            const int mat_stride = P.q_chunk_bytes + P.d_chunk_bytes;
-            while (u < u_end) {
-                const Chunk ch = next_chunk(P, u, u_end);
-                const int slot = it % NS;
-                if (it >= NS) {
-                    mbar_wait(&empty_bar[slot], ((it / NS) - 1) & 1);
-                    finish(slot);
+            int ready = (lane == 0) ? *(volatile int *)hold : 0;
+            ready = __shfl_sync(0xffffffffu, ready, 0);
+            // `p` is the phase of the next chunk (or an earlier phase still to be skipped): chunks of phase q are only requested once
+            // the math warps have put their input loads for phase q on the wire, so those loads never queue behind bulk data
+            if (A.hold_mode != 2) ready = 0x7fffffff;
+            int held1 = (lane == 0 && A.hold_mode == 1) ? *(volatile int *)&hold1_flag : 0;
+            held1 = __shfl_sync(0xffffffffu, held1, 0);
+            if (!all_issued && issued - finished < NS && !held1 && (have_phase ? p <= ready : true)) {
+                while (!have_phase && p < A.n_phases) {   // advance to the next GEMV phase that has work for this CTA
+                    const MegaPhase &P = A.phases[p];
+                    if (P.kind == PH_GEMV) {
+                        tile_band(P.total_units, blockIdx.x, G, u, u_end);
+                        if (u < u_end) { have_phase = true; break; }
+                        if (lane == 0) phase_arrive(A.bar, p);   // nothing of this phase lands here: arrive right away
+                    }
+                    p++;
                 }
+                if (!have_phase) { all_issued = true; continue; }
+                if (p > ready) { __nanosleep(32); continue; }   // found the next phase with work, but its input is not requested yet
+                const MegaPhase &P = A.phases[p];
+                const Chunk ch = next_chunk(P, u, u_end);
+                const int slot = issued % NS;
                 if (lane == 0) {
-                    pend_phase[slot] = p; pend_seg[slot] = ch.seg; pend_row0[slot] = ch.row0; pend_rows[slot] = ch.rows; pend_last[slot] = (u == u_end);
                     const StreamSeg &sg = P.seg[ch.seg];
+                    pend[slot] = Pend{sg.out, sg.bias, p, ch.row0, ch.rows, (int)(u == u_end), P.RG, P.nb_pad >> 5, P.upc, P.NM, P.epi, P.out_reps, P.out_stride};
+                    const uint32_t mat_stride = P.q_chunk_bytes + P.d_chunk_bytes;
                     const uint32_t qb = (uint32_t)ch.rows * P.nb * QB, db = (uint32_t)ch.rows * P.nb * DB;
                     uint8_t *st = smem + (size_t)slot * A.slot_bytes;
                     mbar_expect_tx(&full_bar[slot], (qb + db) * P.NM);
@@ -558,15 +627,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
                     }
                 }
                 __syncwarp();
-                it++;
+                issued++;
+                if (u == u_end) { have_phase = false; p++; }
+                progress = true;
             }
-        }
-        // drain: the last min(it, NS) chunks still await their epilogue, oldest first
-        const int total = it;
-        for (int j = (total > NS ? total - NS : 0); j < total; j++) {
-            const int slot = j % NS;
-            mbar_wait(&empty_bar[slot], (j / NS) & 1);
-            finish(slot);
+            if (!progress) {
+                if (finished < issued) {   // nothing to issue right now: block on the oldest chunk and finish it the moment it is consumed
+                    const int slot = finished % NS;
+                    mbar_wait(&empty_bar[slot], (finished / NS) & 1);
+                    finish(slot);
+                    finished++;
+                } else {
+                    __nanosleep(32);
+                }
+            }
         }
         return;
     }
@@ -574,14 +648,20 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
     // ===================== consumer warps =====================
     int it = 0;
     for (int p = 0; p < A.n_phases; p++) {
-        const MegaPhase &P = A.phases[p];
-        if (tid == 0) MG_TRACE(p, 0);
-        if (p > 0) {  // inputs of phase p are complete when every CTA has arrived on phase p-1
-            if (tid == 0) phase_wait(A.bar, p - 1, (unsigned)G);   // one poller per CTA
-            mega_consumer_bar();
+        // the (immutable) phase descriptor is fetched into shared memory while we wait for the previous phase to complete, so no
+        // L2 round trip for it sits between the barrier and the first use
+        if (warp == 1) {
+            const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.phases[p]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sph[p & 1]);
+            for (int i = lane; i < (int)(sizeof(MegaPhase) / 4); i += 32) dst[i] = __ldg(src + i);
         }
+        const MegaPhase &P = sph[p & 1];
+        if (tid == 0) { MG_TRACE(p, 0); if (p > 0) *(volatile int *)&hold1_flag = 1; }
+        if (p > 0 && tid == 0) phase_wait(A.bar, p - 1, (unsigned)G);   // inputs of phase p are complete when every CTA arrived on p-1
+        mega_consumer_bar();
         if (tid == 0) MG_TRACE(p, 1);
         if (P.kind == PH_ATTN) {
+            if (tid == 0) { *(volatile int *)&hold_flag = p; *(volatile int *)&hold1_flag = 0; }
             const int n_items = A.at.n_kv_heads * A.at.nsplit;
             for (int item = blockIdx.x; item < n_items; item += G) attn_item(A.at, P.layer, item, att, tid);
             __threadfence();
@@ -589,8 +669,8 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
             if (tid == 0) { MG_TRACE(p, 3); phase_arrive(A.bar, p); MG_TRACE(p, 4); }
             continue;
         }
-        if (P.NM == 2) consume_phase<TYPE, 2>(A, P, smem, full_bar, empty_bar, red, ss_red, &inv_s, xs_buf, it, warp, lane);
-        else consume_phase<TYPE, 1>(A, P, smem, full_bar, empty_bar, red, ss_red, &inv_s, xs_buf, it, warp, lane);
+        if (P.NM == 2) consume_phase<TYPE, 2>(A, P, smem, full_bar, empty_bar, red, ss_red, &inv_s, xs_buf, &hold_flag, &hold1_flag, it, warp, lane, p);
+        else consume_phase<TYPE, 1>(A, P, smem, full_bar, empty_bar, red, ss_red, &inv_s, xs_buf, &hold_flag, &hold1_flag, it, warp, lane, p);
         if (tid == 0) MG_TRACE(p, 3);
     }
 }
