@@ -170,8 +170,17 @@ def main():
     tps = args.tokens_per_step
     seq_len = min(2048, PROMPT_LEN + tps + 8)
     gf = T.SyntheticGGUF(args.tier, typ, seed=0, seq_len=seq_len)
+    # N > 1: tensor parallel over the N GPUs when the tier shards evenly (big: 2/4/8, large: 2/4), else independent replicas
+    tp = 1
+    if world > 1:
+        from nanollama_b200.tp import shard_plan
+        try:
+            shard_plan(gf.meta, world)
+            tp = world
+        except ValueError:
+            tp = 1
     t0 = time.time()
-    m = M.load_llama_model(gf, device=local_rank)
+    m = M.load_llama_model(gf, device=local_rank, tp_rank=rank if tp > 1 else 0, tp_size=tp)
     load_s = time.time() - t0
     rng = np.random.default_rng(5)
     prompt = np.concatenate([[1], rng.integers(3, gf.meta.vocab_size, size=PROMPT_LEN - 1)]).astype(np.int32)
@@ -201,7 +210,8 @@ def main():
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         ms_total = float(t.item())
     ms_per_step = ms_total / args.steps
-    value = world * tps * args.steps / (ms_total / 1000.0)  # replicas: every rank decodes its own sequence
+    n_seq = 1 if tp > 1 else world   # tensor parallel: one sequence on all GPUs; replicas: every rank decodes its own sequence
+    value = n_seq * tps * args.steps / (ms_total / 1000.0)
 
     # ---- end-to-end arm: Forward(token,pos) -> host logits -> host argmax, per token ----
     def e2e_step():
@@ -224,22 +234,40 @@ def main():
         t = torch.tensor([e2e_s], device="cuda")
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
         e2e_s = float(t.item())
-    e2e_value = world * tps * e2e_steps / e2e_s
+    e2e_value = n_seq * tps * e2e_steps / e2e_s
 
-    # ---- roofline of the dominant kernel (dequant-fused GEMV): algorithmic bytes / time ----
+    # ---- roofline of the dominant kernel family (the dequant-fused streaming GEMV: >95 % of the step, profiles/r01_launches_big.md) ----
+    # achieved = algorithmic bytes of one decode step (weights + one embedding row + norm weights + KV read/write at
+    # the mid position of the step) / CUDA-event time of that step, i.e. every launch gap, the attention and the argmax kernels are
+    # charged to the GEMV too -- a lower bound of the kernel's own bandwidth.  The kernel alone, back to back on the largest
+    # matrix of the tier with L2-cold replicas (CUDA events inside nl_matrix_bench), is reported next to it as `kernel_alone`.
     peak, peak_src = load_peaks()
     mid_pos = PROMPT_LEN - 1 + tps // 2
     bytes_tok = T.decode_bytes_per_token(gf.meta, typ, mid_pos)
     weight_only = T.BPE[typ] * T.matmul_params(gf.meta)
-    achieved = bytes_tok / (ms_per_step / 1000.0 / tps) / 1e9
+    achieved = (bytes_tok / tp) / (ms_per_step / 1000.0 / tps) / 1e9   # per-GPU stream: each rank reads 1/tp of the weights
+    alone = None
+    try:
+        raw, info = gf.get_tensor("output.weight")
+        rows, cols = info.rows_cols
+        dm = M.DeviceMatrix(raw, typ, rows, cols, device=local_rank)
+        nbytes = raw.size
+        copies = max(2, int(300e6 // nbytes) + 1)      # rotate over > 2x L2 worth of weights
+        ms = dm.bench(batch=1, n_copies=copies, warmup=5, iters=40)
+        alone = {"shape": [rows, cols], "bytes": int(nbytes + 4 * cols + 4 * rows), "ms": ms, "GBps": (nbytes + 4 * cols + 4 * rows) / ms / 1e6,
+                 "frac": (nbytes + 4 * cols + 4 * rows) / ms / 1e6 / peak}
+        dm.close()
+    except Exception as e:  # never let the extra measurement kill the bench line
+        alone = {"error": str(e)}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src,
-                "how": "whole decode step: algorithmic bytes per token (weights + norms + KV at mid position, SURVEY §8d) / CUDA-event time per token; "
-                       f"GEMV launches carry {weight_only / bytes_tok:.3f} of those bytes"}
+                "peak_source": peak_src, "kernel": "gemv_stream_kernel (dequant-fused GEMV family)",
+                "bytes_per_step": int(bytes_tok), "gemv_share_of_bytes": weight_only / bytes_tok, "kernel_alone": alone,
+                "how": "algorithmic bytes per decode step / CUDA-event time per step (lower bound of the kernel's bandwidth); "
+                       "kernel_alone = LM-head GEMV timed back to back on L2-cold replicas"}
 
     out = {"metric": metric, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
-           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "weak", "vs_baseline": None, "dtype": "f32",
-           "data": "synthetic", "config": dict(config, parallelism=f"replicas x{world}" if world > 1 else "single GPU", load_s=round(load_s, 1)),
+           "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None, "dtype": "f32",
+           "data": "synthetic", "config": dict(config, parallelism=(f"tp{tp} (column-split q/k/v/gate/up, row-split o/down, vocab-split LM head, one-shot NVLink all-reduce x{2 * gf.meta.num_layers}/token)" if tp > 1 else f"replicas x{world}" if world > 1 else "single GPU"), load_s=round(load_s, 1)),
            "clocks": clocks, "roofline": roofline,
            "e2e": {"value": e2e_value, "unit": "tok/s", "h2d_bytes_per_step": 8 * tps, "d2h_bytes_per_step": 4 * gf.meta.vocab_size * tps},
            "gpu_launches": m.launches_per_token * tps * args.steps, "wall_s": round(wall, 3)}

@@ -13,6 +13,7 @@
 #include "nl_kernels.cuh"
 #include "nl_stream.cuh"
 #include "nl_mega.cuh"
+#include "nl_tp.cuh"
 
 namespace nl {
 
@@ -228,6 +229,12 @@ struct nl_model {
     int64_t weight_bytes = 0;
     cudaEvent_t ev0 = nullptr, ev1 = nullptr;
     GemvOpts opts{148, true, true};
+    // tensor parallelism (one process per GPU): local shard sizes and the NVLink exchange window
+    int tp = 1, rank = 0, nH = 0, nKV = 0, ffn = 0, lvocab = 0;
+    float *partial = nullptr, *logits_local = nullptr;
+    uint8_t *tp_win = nullptr; TpLayout tp_lay{}; TpPeers tp_peers{}; bool tp_ready = false;
+    unsigned int *d_ar_epoch = nullptr, *d_lg_epoch = nullptr;
+    DevMat lm_view;   // this rank's vocab rows of the LM head (a view into output / tok_embd when tied; never freed)
     // per-token persistent kernel (batch 1)
     bool mega_ok = false;
     MegaPhase *d_phases = nullptr; unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;
@@ -296,7 +303,7 @@ static int build_mega(nl_model *m) {
     const nl_config &c = m->c;
     m->mega_ok = false;
     // Opt-in (NL_MEGA=1): on B200 the persistent kernel currently trails the PDL-chained per-matrix kernels
-    if (!getenv("NL_MEGA") || getenv("NL_NO_MEGA")) return NL_OK;
+    if (!getenv("NL_MEGA") || getenv("NL_NO_MEGA") || m->tp > 1) return NL_OK;
     const int type = m->L[0].wq.type;
     if (type != NL_Q4_0 && type != NL_Q8_0 && type != NL_F16) return NL_OK;
     if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
@@ -364,7 +371,8 @@ static int build_mega(nl_model *m) {
 static int record_forward(nl_model *m, int batch) {
     const nl_config &c = m->c;
     cudaStream_t st = m->st;
-    const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = c.interm_size;
+    const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = m->ffn;   // shard sizes when tp > 1
+    const bool tpar = m->tp > 1;
     int launches = 0;
     {   // 1. embedding (+gamma), model.go:500-507
         dim3 grid((dim + 255) / 256, batch);
@@ -397,16 +405,20 @@ static int record_forward(nl_model *m, int batch) {
             a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
             a.seq_stride = (int64_t)c.n_layers * S * kvd;
             a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.pos = m->d_pos; a.out = m->xb2;
-            a.n_heads = c.n_heads; a.n_kv_heads = c.n_kv_heads; a.seq_len = S; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate;
+            a.n_heads = m->nH; a.n_kv_heads = m->nKV; a.seq_len = S; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate;
             a.eps = c.rms_norm_eps; a.scale = (float)(1.0 / sqrt((double)hd));
-            dim3 grid(c.n_heads, batch);
+            dim3 grid(m->nH, batch);
             if (hd == 64) attn_decode_kernel<64><<<grid, 128, S * sizeof(float), st>>>(a);
             else attn_decode_kernel<128><<<grid, 128, S * sizeof(float), st>>>(a);
             launches++;
         }
         {   // output projection + residual, model.go:590-594
-            MatRef r = {&ly.wo, nullptr, ly.bo, m->x, dim};
-            int rc = gemv_dispatch(&r, 1, m->xb2, qdim, batch, EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
+            MatRef r = {&ly.wo, nullptr, ly.bo, tpar ? m->partial : m->x, dim};
+            int rc = gemv_dispatch(&r, 1, m->xb2, qdim, batch, tpar ? EPI_STORE : EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
+            if (tpar) {   // X += sum over ranks of the partial products (row-split WO), one-shot over NVLink peer memory
+                tp_allreduce_resid_kernel<<<1, 1024, 0, st>>>(m->partial, m->x, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_ar_epoch);
+                launches++;
+            }
         }
         {   // FFN pre-norm + gate/up + SiLU*up, model.go:597-606
             const int gt = ly.wgate.type;
@@ -424,14 +436,22 @@ static int record_forward(nl_model *m, int batch) {
             }
         }
         {   // down projection + residual, model.go:609-612
-            MatRef r = {&ly.wdown, nullptr, nullptr, m->x, dim};
-            int rc = gemv_dispatch(&r, 1, m->hb, ffn, batch, EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
+            MatRef r = {&ly.wdown, nullptr, nullptr, tpar ? m->partial : m->x, dim};
+            int rc = gemv_dispatch(&r, 1, m->hb, ffn, batch, tpar ? EPI_STORE : EPI_RESID, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;
+            if (tpar) {
+                tp_allreduce_resid_kernel<<<1, 1024, 0, st>>>(m->partial, m->x, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_ar_epoch);
+                launches++;
+            }
         }
     }
     {   // final norm + LM head, model.go:616-619
-        const DevMat &out = m->output.present() ? m->output : m->tok_embd;
-        MatRef r = {&out, nullptr, nullptr, m->logits, c.vocab_size};
+        const DevMat &out = tpar ? m->lm_view : (m->output.present() ? m->output : m->tok_embd);
+        MatRef r = {&out, nullptr, nullptr, tpar ? m->logits_local : m->logits, tpar ? m->lvocab : c.vocab_size};
         int rc = gemv_dispatch(&r, 1, m->x, dim, batch, EPI_STORE, m->output_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
+        if (tpar) {   // vocab-split LM head: every rank drops its shard into every window (m->logits points into this rank's window)
+            tp_allgather_logits_kernel<<<1, 1024, 0, st>>>(m->logits_local, m->lvocab, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_lg_epoch);
+            launches++;
+        }
     }
     NL_CUDA(cudaGetLastError());
     m->launches_fwd = launches;
@@ -512,12 +532,23 @@ int nl_create(const nl_config *cfg, nl_model **out) {
     if (c.n_heads % c.n_kv_heads) return fail(NL_ERR_INVALID, "n_heads %d not a multiple of n_kv_heads %d", c.n_heads, c.n_kv_heads);
     if (c.head_dim != 64 && c.head_dim != 128) return fail(NL_ERR_UNSUPPORTED, "head_dim %d (supported: 64, 128)", c.head_dim);
     if (c.embed_dim % 32 || c.interm_size % 32) return fail(NL_ERR_INVALID, "embed_dim/interm_size must be multiples of 32");
-    if (c.tp_size != 1) return fail(NL_ERR_UNSUPPORTED, "tp_size %d: tensor parallelism is not built yet", c.tp_size);
+    if (c.tp_size != 1 && c.tp_size != 2 && c.tp_size != 4 && c.tp_size != 8) return fail(NL_ERR_INVALID, "tp_size %d (supported: 1, 2, 4, 8)", c.tp_size);
+    if (c.tp_rank < 0 || c.tp_rank >= c.tp_size) return fail(NL_ERR_INVALID, "tp_rank %d out of range [0,%d)", c.tp_rank, c.tp_size);
+    if (c.tp_size > 1) {
+        const int n = c.tp_size;
+        // column-split q/k/v/gate/up by heads / ffn rows, row-split o/down along whole 32-element blocks, vocab-split LM head
+        if (c.n_heads % n || c.n_kv_heads % n) return fail(NL_ERR_INVALID, "tp_size %d does not divide n_heads %d / n_kv_heads %d evenly", n, c.n_heads, c.n_kv_heads);
+        if (c.interm_size % (32 * n) || (c.n_heads / n * c.head_dim) % 32) return fail(NL_ERR_INVALID, "tp_size %d: shard boundaries would cut a 32-element quant block", n);
+        if (c.vocab_size % (4 * n)) return fail(NL_ERR_INVALID, "tp_size %d does not divide vocab_size %d into float4-aligned shards", n, c.vocab_size);
+        if (c.max_batch != 1) return fail(NL_ERR_UNSUPPORTED, "tensor parallelism is built for batch 1");
+    }
     if (c.max_batch > 64) return fail(NL_ERR_INVALID, "max_batch %d > 64", c.max_batch);
     int rc = check_device(c.device);
     if (rc) return rc;
     nl_model *m = new nl_model();
     m->c = c; m->dim = c.embed_dim; m->hd = c.head_dim; m->kvd = c.n_kv_heads * c.head_dim; m->qdim = c.n_heads * c.head_dim; m->B = c.max_batch;
+    m->tp = c.tp_size; m->rank = c.tp_rank; m->nH = c.n_heads / m->tp; m->nKV = c.n_kv_heads / m->tp; m->ffn = c.interm_size / m->tp; m->lvocab = c.vocab_size / m->tp;
+    m->qdim = m->nH * c.head_dim; m->kvd = m->nKV * c.head_dim;   // from here on qdim / kvd / ffn are this rank's shard sizes
     m->L.resize(c.n_layers);
     m->opts = default_opts(c.device);
     cudaError_t e = cudaStreamCreateWithFlags(&m->st, cudaStreamNonBlocking);
@@ -537,34 +568,61 @@ int nl_upload_tensor(nl_model *m, int slot, int layer, uint32_t type, int64_t ro
     if (m->finalized) return fail(NL_ERR_STATE, "upload after nl_finalize");
     int rc = set_dev(m); if (rc) return rc;
     const nl_config &c = m->c;
-    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size;
+    // shapes of the FULL tensors as they sit in the GGUF; with tp_size > 1 only this rank's shard is kept
+    const int dim = m->dim, kvd = c.n_kv_heads * c.head_dim, qdim = c.n_heads * c.head_dim, ffn = c.interm_size;
+    const int tp = m->tp, rk = m->rank;
     if (slot >= NL_ATTN_NORM && (layer < 0 || layer >= c.n_layers)) return fail(NL_ERR_INVALID, "layer %d out of range", layer);
     Layer *ly = slot >= NL_ATTN_NORM ? &m->L[layer] : nullptr;
     DevMat *mat = nullptr; float **vec = nullptr; int64_t er = 1, ec = 0;
+    enum { FULL, ROWS, COLS } split = FULL;
     switch (slot) {
-    case NL_TOK_EMBD: mat = &m->tok_embd; er = c.vocab_size; ec = dim; break;
-    case NL_OUTPUT: mat = &m->output; er = c.vocab_size; ec = dim; break;
+    case NL_TOK_EMBD: mat = &m->tok_embd; er = c.vocab_size; ec = dim; break;             // any token may be looked up: kept whole
+    case NL_OUTPUT: mat = &m->output; er = c.vocab_size; ec = dim; split = ROWS; break;
     case NL_OUTPUT_NORM: vec = &m->output_norm; ec = dim; break;
     case NL_ATTN_NORM: vec = &ly->attn_norm; ec = dim; break;
     case NL_FFN_NORM: vec = &ly->ffn_norm; ec = dim; break;
-    case NL_WQ: mat = &ly->wq; er = qdim; ec = dim; break;
-    case NL_WK: mat = &ly->wk; er = kvd; ec = dim; break;
-    case NL_WV: mat = &ly->wv; er = kvd; ec = dim; break;
-    case NL_WO: mat = &ly->wo; er = dim; ec = qdim; break;
-    case NL_WGATE: mat = &ly->wgate; er = ffn; ec = dim; break;
-    case NL_WUP: mat = &ly->wup; er = ffn; ec = dim; break;
-    case NL_WDOWN: mat = &ly->wdown; er = dim; ec = ffn; break;
-    case NL_BQ: vec = &ly->bq; ec = qdim; break;
-    case NL_BK: vec = &ly->bk; ec = kvd; break;
-    case NL_BV: vec = &ly->bv; ec = kvd; break;
+    case NL_WQ: mat = &ly->wq; er = qdim; ec = dim; split = ROWS; break;
+    case NL_WK: mat = &ly->wk; er = kvd; ec = dim; split = ROWS; break;
+    case NL_WV: mat = &ly->wv; er = kvd; ec = dim; split = ROWS; break;
+    case NL_WO: mat = &ly->wo; er = dim; ec = qdim; split = COLS; break;
+    case NL_WGATE: mat = &ly->wgate; er = ffn; ec = dim; split = ROWS; break;
+    case NL_WUP: mat = &ly->wup; er = ffn; ec = dim; split = ROWS; break;
+    case NL_WDOWN: mat = &ly->wdown; er = dim; ec = ffn; split = COLS; break;
+    case NL_BQ: vec = &ly->bq; ec = qdim; split = ROWS; break;
+    case NL_BK: vec = &ly->bk; ec = kvd; split = ROWS; break;
+    case NL_BV: vec = &ly->bv; ec = kvd; split = ROWS; break;
     case NL_BO: vec = &ly->bo; ec = dim; break;
     default: return fail(NL_ERR_INVALID, "unknown tensor slot %d", slot);
     }
+    if (tp == 1) split = FULL;
     if (vec) {
         if (rows * cols != ec) return fail(NL_ERR_INVALID, "slot %d: %lld elements, expected %lld", slot, (long long)(rows * cols), (long long)ec);
-        return upload_vec(vec, (int)type, ec, host, nbytes, m->st);
+        if (slot == NL_BO && rk != 0) return NL_OK;   // the output-projection bias is added once, by rank 0
+        rc = upload_vec(vec, (int)type, ec, host, nbytes, m->st);
+        if (rc || split == FULL) return rc;
+        const int64_t ln = ec / tp;                    // keep elements [rk*ln, (rk+1)*ln)
+        float *shard = nullptr;
+        NL_CUDA(cudaMalloc(&shard, ln * 4));
+        NL_CUDA(cudaMemcpy(shard, *vec + rk * ln, ln * 4, cudaMemcpyDeviceToDevice));
+        cudaFree(*vec); *vec = shard;
+        return NL_OK;
     }
     if (rows != er || cols != ec) return fail(NL_ERR_INVALID, "slot %d: shape %lldx%lld, expected %lldx%lld", slot, (long long)rows, (long long)cols, (long long)er, (long long)ec);
+    if (!type_supported((int)type)) return fail(NL_ERR_UNSUPPORTED, "unsupported tensor type %u", type);
+    if ((int64_t)nbytes != tensor_nbytes((int)type, rows * cols)) return fail(NL_ERR_INVALID, "tensor has %zu bytes, expected %lld", nbytes, (long long)tensor_nbytes((int)type, rows * cols));
+    const int64_t row_bytes = cols / blk_elems((int)type) * blk_bytes((int)type);
+    if (split == ROWS) {
+        const int64_t lr = rows / tp;
+        return upload_mat(*mat, (int)type, lr, cols, (const uint8_t *)host + rk * lr * row_bytes, (size_t)(lr * row_bytes), m->st);
+    }
+    if (split == COLS) {   // whole quant blocks [rk*lc/be, (rk+1)*lc/be) of every row, gathered on the host
+        const int64_t lc = cols / tp;
+        if (lc % blk_elems((int)type)) return fail(NL_ERR_INVALID, "column shard %lld cuts a quant block of type %u", (long long)lc, type);
+        const int64_t lb = lc / blk_elems((int)type) * blk_bytes((int)type);
+        std::vector<uint8_t> tmp((size_t)(rows * lb));
+        for (int64_t r = 0; r < rows; r++) memcpy(tmp.data() + r * lb, (const uint8_t *)host + r * row_bytes + rk * lb, (size_t)lb);
+        return upload_mat(*mat, (int)type, rows, lc, tmp.data(), tmp.size(), m->st);
+    }
     return upload_mat(*mat, (int)type, rows, cols, host, nbytes, m->st);
 }
 
@@ -601,17 +659,17 @@ int nl_finalize(nl_model *m) {
                          : !ly.wup.present() ? "ffn_up" : !ly.wdown.present() ? "ffn_down" : nullptr;
         if (miss) return fail(NL_ERR_STATE, "layer %d %s: tensor not uploaded", l, miss);
     }
-    const int B = m->B, dim = m->dim, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, half = m->hd / 2;
+    const int B = m->B, dim = m->dim, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, half = m->hd / 2, ffn = m->ffn;
     auto alloc = [&](float **p, size_t n) -> int { NL_CUDA(cudaMalloc(p, n * 4)); NL_CUDA(cudaMemset(*p, 0, n * 4)); return NL_OK; };
     {   // x, xb2 and hb double as the replicated activation vectors of the persistent batch-1 kernel
-        int mx = dim > qdim ? dim : qdim; if (c.interm_size > mx) mx = c.interm_size;
+        int mx = dim > qdim ? dim : qdim; if (ffn > mx) mx = ffn;
         m->act_stride = (mx + 31) / 32 * 32;
     }
     const size_t rep_floats = (size_t)MG_REPS * m->act_stride;
     auto mx2 = [](size_t a, size_t b) { return a > b ? a : b; };
     if ((rc = alloc(&m->x, mx2((size_t)B * dim, rep_floats))) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, mx2((size_t)B * qdim, rep_floats))) ||
-        (rc = alloc(&m->hb, mx2((size_t)B * c.interm_size, rep_floats))) || (rc = alloc(&m->hb2, (size_t)B * c.interm_size)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
-        (rc = alloc(&m->k, (size_t)B * kvd)) || (rc = alloc(&m->v, (size_t)B * kvd)) || (rc = alloc(&m->logits, (size_t)B * c.vocab_size)) ||
+        (rc = alloc(&m->hb, mx2((size_t)B * ffn, rep_floats))) || (rc = alloc(&m->hb2, (size_t)B * ffn)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
+        (rc = alloc(&m->k, (size_t)B * kvd)) || (rc = alloc(&m->v, (size_t)B * kvd)) || (m->tp == 1 && (rc = alloc(&m->logits, (size_t)B * c.vocab_size))) ||
         (rc = alloc(&m->kc, (size_t)B * c.n_layers * S * kvd)) || (rc = alloc(&m->vc, (size_t)B * c.n_layers * S * kvd)))
         return rc;
     // RoPE tables: float64 pow/cos/sin rounded to fp32 (go/model.go:346-358)
@@ -638,6 +696,30 @@ int nl_finalize(nl_model *m) {
     for (auto &ly : m->L) wb += ly.wq.bytes() + ly.wk.bytes() + ly.wv.bytes() + ly.wo.bytes() + ly.wgate.bytes() + ly.wup.bytes() + ly.wdown.bytes() + 2 * (int64_t)dim * 4;
     m->weight_bytes = wb;
     if (S * sizeof(float) > 48 * 1024) return fail(NL_ERR_INVALID, "seq_len too large for the attention kernel");
+    if (m->tp > 1) {
+        // exchange window (exported to the peers with CUDA IPC), partial-product buffer, local logits shard
+        m->tp_lay = tp_layout(m->tp, dim, c.vocab_size);
+        NL_CUDA(cudaMalloc(&m->tp_win, m->tp_lay.total));
+        NL_CUDA(cudaMemset(m->tp_win, 0, m->tp_lay.total));
+        m->logits = reinterpret_cast<float *>(m->tp_win + m->tp_lay.lg_data);
+        if ((rc = alloc(&m->partial, (size_t)dim)) || (rc = alloc(&m->logits_local, (size_t)m->lvocab))) return rc;
+        NL_CUDA(cudaMalloc(&m->d_ar_epoch, 4)); NL_CUDA(cudaMalloc(&m->d_lg_epoch, 4));
+        NL_CUDA(cudaMemset(m->d_ar_epoch, 0, 4)); NL_CUDA(cudaMemset(m->d_lg_epoch, 0, 4));
+        // LM head shard: uploaded output.weight is already this rank's rows; a tied embedding is viewed at its vocab slice
+        if (m->output.present()) m->lm_view = m->output;
+        else {
+            const DevMat &e = m->tok_embd;
+            m->lm_view = e; m->lm_view.rows = m->lvocab;
+            if (e.type == NL_Q4_0 || e.type == NL_Q8_0) {
+                const int64_t nb = (int64_t)m->rank * m->lvocab * (e.cols / 32);
+                m->lm_view.qs = e.qs + nb * (e.type == NL_Q4_0 ? 16 : 32); m->lm_view.d = e.d + nb;
+            } else {
+                m->lm_view.qs = e.qs + (int64_t)m->rank * m->lvocab * (e.cols / blk_elems(e.type)) * blk_bytes(e.type);
+            }
+        }
+        m->finalized = true;   // graphs are captured by nl_tp_import_handles once the peers' windows are mapped
+        return NL_OK;
+    }
     rc = build_mega(m);
     if (rc) return rc;
     rc = build_graphs(m, 1);
@@ -661,6 +743,15 @@ void nl_destroy(nl_model *m) {
     for (float *p : fs) if (p) cudaFree(p);
     int32_t *is[] = {m->gamma_map, m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->d_prompt, m->d_cursor};
     for (int32_t *p : is) if (p) cudaFree(p);
+    if (m->tp > 1) {
+        for (int r = 0; r < m->tp; r++) if (r != m->rank && m->tp_peers.win[r]) cudaIpcCloseMemHandle(m->tp_peers.win[r]);
+        if (m->tp_win) cudaFree(m->tp_win);
+        m->logits = nullptr;   // lived inside the window
+        if (m->partial) cudaFree(m->partial);
+        if (m->logits_local) cudaFree(m->logits_local);
+        if (m->d_ar_epoch) cudaFree(m->d_ar_epoch);
+        if (m->d_lg_epoch) cudaFree(m->d_lg_epoch);
+    }
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->d_phases) cudaFree(m->d_phases);
     if (m->d_bar) cudaFree(m->d_bar);
@@ -677,6 +768,7 @@ void nl_destroy(nl_model *m) {
 static int ready(nl_model *m) {
     if (!m) return fail(NL_ERR_INVALID, "null model");
     if (!m->finalized) return fail(NL_ERR_STATE, "model not finalized");
+    if (m->tp > 1 && !m->tp_ready) return fail(NL_ERR_STATE, "tensor-parallel model: nl_tp_import_handles has not been called");
     return set_dev(m);
 }
 
@@ -936,7 +1028,38 @@ int nl_matmul(uint32_t type, const void *host_w, int64_t rows, int64_t cols, con
     return rc;
 }
 
-int nl_tp_export_handle(nl_model *m, void *handle64) { (void)m; (void)handle64; return fail(NL_ERR_UNSUPPORTED, "tensor parallelism is not built yet"); }
-int nl_tp_import_handles(nl_model *m, const void *h, int32_t n) { (void)m; (void)h; (void)n; return fail(NL_ERR_UNSUPPORTED, "tensor parallelism is not built yet"); }
+int nl_tp_export_handle(nl_model *m, void *handle64) {
+    if (!m || !handle64) return fail(NL_ERR_INVALID, "null argument");
+    if (m->tp <= 1) return fail(NL_ERR_STATE, "model is not tensor-parallel (tp_size == 1)");
+    if (!m->finalized || !m->tp_win) return fail(NL_ERR_STATE, "nl_finalize first");
+    int rc = set_dev(m); if (rc) return rc;
+    static_assert(sizeof(cudaIpcMemHandle_t) == 64, "CUDA IPC handle is 64 bytes");
+    cudaIpcMemHandle_t hnd;
+    NL_CUDA(cudaIpcGetMemHandle(&hnd, m->tp_win));
+    memcpy(handle64, &hnd, 64);
+    return NL_OK;
+}
+
+int nl_tp_import_handles(nl_model *m, const void *handles64_by_rank, int32_t n_ranks) {
+    if (!m || !handles64_by_rank) return fail(NL_ERR_INVALID, "null argument");
+    if (m->tp <= 1) return fail(NL_ERR_STATE, "model is not tensor-parallel (tp_size == 1)");
+    if (n_ranks != m->tp) return fail(NL_ERR_INVALID, "%d handles for tp_size %d", n_ranks, m->tp);
+    if (!m->finalized || !m->tp_win) return fail(NL_ERR_STATE, "nl_finalize first");
+    if (m->tp_ready) return fail(NL_ERR_STATE, "peer windows already imported");
+    int rc = set_dev(m); if (rc) return rc;
+    for (int r = 0; r < m->tp; r++) {
+        if (r == m->rank) { m->tp_peers.win[r] = m->tp_win; continue; }
+        cudaIpcMemHandle_t hnd;
+        memcpy(&hnd, (const uint8_t *)handles64_by_rank + 64 * r, 64);
+        void *p = nullptr;
+        cudaError_t e = cudaIpcOpenMemHandle(&p, hnd, cudaIpcMemLazyEnablePeerAccess);
+        if (e != cudaSuccess) return fail(NL_ERR_CUDA, "cudaIpcOpenMemHandle(rank %d): %s", r, cudaGetErrorString(e));
+        m->tp_peers.win[r] = (uint8_t *)p;
+    }
+    m->tp_ready = true;
+    rc = build_graphs(m, 1);
+    if (rc) { m->tp_ready = false; return rc; }
+    return NL_OK;
+}
 
 }  // extern "C"

@@ -134,13 +134,18 @@ class LlamaModel:
 
 
 def load_llama_model(gf: GGUFFile, device: int = 0, max_batch: int = 1, verbose: bool = False,
-                     rope_conjugate: Optional[bool] = None, qk_norm: Optional[bool] = None) -> LlamaModel:
-    """go/model.go:121-174 + loadWeights :177-265.  Errors are wrapped like the Go ones ("load weights: layer 3 attn_q: ...")."""
+                     rope_conjugate: Optional[bool] = None, qk_norm: Optional[bool] = None,
+                     tp_rank: int = 0, tp_size: int = 1, exchange=None) -> LlamaModel:
+    """go/model.go:121-174 + loadWeights :177-265.  Errors are wrapped like the Go ones ("load weights: layer 3 attn_q: ...").
+
+    tp_size > 1: this process is rank `tp_rank` of a tensor-parallel group (one process per GPU); every rank passes the FULL
+    tensors and the library keeps its shard.  `exchange(handle_bytes) -> [handle of rank 0, 1, ...]` all-gathers the 64-byte
+    CUDA IPC handles of the ranks' NVLink windows (nanollama_b200.tp.exchange_handles_torch by default)."""
     m = gf.meta
     L = capi.lib()
     cfg = capi.NlConfig(m.num_layers, m.embed_dim, m.num_heads, m.num_kv_heads, m.head_dim, m.vocab_size, m.seq_len, m.interm_size,
                         m.rms_norm_eps, m.rope_theta, int(m.qk_norm if qk_norm is None else qk_norm),
-                        int(m.rope_conjugate if rope_conjugate is None else rope_conjugate), device, 0, 1, max_batch)
+                        int(m.rope_conjugate if rope_conjugate is None else rope_conjugate), device, tp_rank, tp_size, max_batch)
     h = C.c_void_p()
     capi.check(L.nl_create(C.byref(cfg), C.byref(h)))
     try:
@@ -172,6 +177,16 @@ def load_llama_model(gf: GGUFFile, device: int = 0, max_batch: int = 1, verbose:
         except (KeyError, capi.NlError) as e:
             raise RuntimeError(f"load weights: {e}") from e
         capi.check(L.nl_finalize(h))
+        if tp_size > 1:
+            if exchange is None:
+                from .tp import exchange_handles_torch as exchange
+            mine = C.create_string_buffer(64)
+            capi.check(L.nl_tp_export_handle(h, mine))
+            handles = exchange(mine.raw)
+            if len(handles) != tp_size or any(len(x) != 64 for x in handles):
+                raise RuntimeError("tensor-parallel handle exchange returned a malformed list")
+            blob = C.create_string_buffer(b"".join(handles), 64 * tp_size)
+            capi.check(L.nl_tp_import_handles(h, blob, tp_size))
         out = capi.NlConfig()
         capi.check(L.nl_get_config(h, C.byref(out)))
     except Exception:

@@ -302,3 +302,18 @@ def test_tier_greedy_256_identical(tier, typ, n_new):
         m.forward(int(seq[pos]), pos)
         assert maxrel(m.state.logits, o.forward(int(seq[pos]), pos)) < LOGIT_TOL
     m.close()
+
+
+# ---------------------------------------------------------------- tensor parallel (needs >= 2 GPUs on the box)
+def test_tensor_parallel_2gpu_parity():
+    import socket
+    import subprocess
+    import sys
+    import torch
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs (run under gpurun --gpus 2)")
+    s = socket.socket(); s.bind(("127.0.0.1", 0)); port = s.getsockname()[1]; s.close()
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
+                        "--master-port", str(port), os.path.join(root, "tests", "tp_worker.py")], capture_output=True, text=True, timeout=900)
+    assert r.returncode == 0 and "TP_PARITY_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
