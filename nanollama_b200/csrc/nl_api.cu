@@ -37,6 +37,7 @@ static void free_mat(DevMat &m) {
 
 // Upload a [rows, cols] tensor from host GGUF bytes into the planar device layout.
 static int upload_mat(DevMat &m, int type, int64_t rows, int64_t cols, const void *host, size_t nbytes, cudaStream_t st) {
+    cudaGetLastError();  // drop a stale (non-sticky) error some other library in the process may have left behind on this thread
     if (!type_supported(type)) return fail(NL_ERR_UNSUPPORTED, "unsupported tensor type %d", type);
     if (rows <= 0 || cols <= 0 || cols % blk_elems(type) != 0) return fail(NL_ERR_INVALID, "bad shape %lldx%lld for type %d", (long long)rows, (long long)cols, type);
     if ((type == NL_F16 && cols % 8) || (type == NL_F32 && cols % 4)) return fail(NL_ERR_INVALID, "cols %lld not a multiple of the 16-byte unit", (long long)cols);
@@ -246,6 +247,7 @@ struct nl_model {
 };
 
 static int set_dev(const nl_model *m) {
+    cudaGetLastError();  // see upload_mat
     NL_CUDA(cudaSetDevice(m->c.device));
     return NL_OK;
 }

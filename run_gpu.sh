@@ -1,3 +1,2 @@
-for cfg in "1 0" "1 1"; do set -- $cfg; echo "REPS=$1 HOLD=$2"; NL_REPS=$1 NL_HOLD=$2 timeout 200 python bench.py --steps 3 --no-cpu-baseline 2>/dev/null | cut -c1-80; done
-NL_REPS=1 NL_HOLD=0 timeout 200 python bench.py --steps 3 --tier mini --no-cpu-baseline 2>/dev/null | cut -c1-80
-timeout 600 python -m pytest tests -m gpu -q -x --timeout 120 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+set -x
+timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node 2 --master-addr 127.0.0.1 --master-port 29511 tests/tp_worker.py > gpurun_out/tp2.log 2>&1; echo "tp2 rc=$?"; grep "\[tp\]\|TP_PARITY\|Error\|error" gpurun_out/tp2.log | tail -12
