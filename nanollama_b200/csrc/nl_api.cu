@@ -14,6 +14,7 @@
 #include "nl_stream.cuh"
 #include "nl_mega.cuh"
 #include "nl_tp.cuh"
+#include "nl_gemm.cuh"
 
 namespace nl {
 
@@ -195,6 +196,26 @@ static int gemv_dispatch(const MatRef *mats, int nmat, const float *x, int x_str
     // mixed types (or SwiGLU over raw-block types): one launch per matrix, SwiGLU as a separate pass
     if (epi == EPI_SWIGLU) return fail(NL_ERR_STATE, "internal: unfused swiglu must be issued by the caller");
     for (int i = 0; i < nmat; i++) { int rc = gemv_multi(&mats[i], 1, xin, x_stride, batch, epi, st); if (rc) return rc; if (launches) (*launches)++; }
+    return NL_OK;
+}
+
+
+// C[T, rows] (=|+=) A[T, cols] · W^T on the tensor cores (nl_gemm.cuh).  a_hi / a_lo: bf16 planes of A, already split.
+static bool gemm_eligible(const DevMat &w) {
+    return (w.type == NL_Q4_0 || w.type == NL_Q8_0 || w.type == NL_F16) && w.cols % GM_BK == 0;
+}
+static int gemm_run(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, const float *bias, float *c, int ldc, int epi, cudaStream_t st) {
+    GemmArgs g; memset(&g, 0, sizeof g);
+    g.a_hi = a_hi; g.a_lo = a_lo; g.qs = w.qs; g.d = w.d; g.bias = bias; g.c = c; g.T = T; g.N = (int)w.rows; g.K = (int)w.cols; g.ldc = ldc; g.epi = epi;
+    g.swap_lbo_sbo = getenv("NL_GEMM_SWAP") ? 1 : 0;
+    int rc = w.type == NL_Q4_0 ? launch_gemm_q4_0(g, st) : w.type == NL_Q8_0 ? launch_gemm_q8_0(g, st) : launch_gemm_f16(g, st);
+    if (rc) return fail(NL_ERR_CUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return NL_OK;
+}
+static int split_planes(const float *x, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t n, cudaStream_t st) {
+    const int64_t pairs = (n + 1) / 2;
+    split_bf16_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
+    NL_CUDA(cudaGetLastError());
     return NL_OK;
 }
 
@@ -941,6 +962,7 @@ struct nl_matrix {
     int device = 0;
     std::vector<DevMat> copies;  // replicas for L2-cold benchmarking; [0] is the matrix
     float *x = nullptr, *out = nullptr; int xcap = 0;
+    __nv_bfloat16 *xh = nullptr, *xl = nullptr;   // bf16 planes of x for the tensor-core path
     cudaStream_t st = nullptr;
     GemvOpts opts{148, true, true};
 };
@@ -962,7 +984,10 @@ int nl_matrix_create(uint32_t type, const void *host_w, int64_t rows, int64_t co
 static int matrix_buffers(nl_matrix *w, int batch) {
     if (batch <= w->xcap) return NL_OK;
     if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
-    w->x = w->out = nullptr;
+    if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
+    w->x = w->out = nullptr; w->xh = w->xl = nullptr;
+    NL_CUDA(cudaMalloc(&w->xh, (size_t)batch * w->copies[0].cols * 2));
+    NL_CUDA(cudaMalloc(&w->xl, (size_t)batch * w->copies[0].cols * 2));
     NL_CUDA(cudaMalloc(&w->x, (size_t)batch * w->copies[0].cols * 4));
     NL_CUDA(cudaMalloc(&w->out, (size_t)batch * w->copies[0].rows * 4));
     w->xcap = batch;
@@ -970,13 +995,20 @@ static int matrix_buffers(nl_matrix *w, int batch) {
 }
 
 int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *host_out) {
-    if (!w || !host_x || !host_out || batch < 1 || batch > 64) return fail(NL_ERR_INVALID, "bad argument");
+    if (!w || !host_x || !host_out || batch < 1 || batch > 4096) return fail(NL_ERR_INVALID, "bad argument");
     NL_CUDA(cudaSetDevice(w->device));
     int rc = matrix_buffers(w, batch); if (rc) return rc;
     const DevMat &m = w->copies[0];
     NL_CUDA(cudaMemcpyAsync(w->x, host_x, (size_t)batch * m.cols * 4, cudaMemcpyHostToDevice, w->st));
-    MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
-    rc = gemv_dispatch(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
+    const int gemm_min = getenv("NL_GEMM_MIN_BATCH") ? atoi(getenv("NL_GEMM_MIN_BATCH")) : 16;
+    if (batch >= gemm_min && gemm_eligible(m)) {   // many rows of x: the T-token GEMM on the tensor cores
+        rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * m.cols, w->st); if (rc) return rc;
+        rc = gemm_run(m, w->xh, w->xl, batch, nullptr, w->out, (int)m.rows, GEPI_STORE, w->st); if (rc) return rc;
+    } else {
+        if (batch > 64) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 64 == 0", batch);
+        MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
+        rc = gemv_dispatch(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
+    }
     NL_CUDA(cudaMemcpyAsync(host_out, w->out, (size_t)batch * m.rows * 4, cudaMemcpyDeviceToHost, w->st));
     NL_CUDA(cudaStreamSynchronize(w->st));
     return NL_OK;
@@ -1017,6 +1049,7 @@ void nl_matrix_destroy(nl_matrix *w) {
     if (w->st) cudaStreamSynchronize(w->st);
     for (auto &c : w->copies) free_mat(c);
     if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
+    if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
     if (w->st) cudaStreamDestroy(w->st);
     delete w;
 }

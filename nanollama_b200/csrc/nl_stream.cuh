@@ -21,6 +21,10 @@ constexpr int ST_CONSUMER_WARPS = 12;
 constexpr int ST_CONSUMERS = ST_CONSUMER_WARPS * 32;  // 384
 constexpr int ST_THREADS = ST_CONSUMERS + 32;         // + producer warp
 constexpr int ST_MAX_STAGES = 8;
+#ifndef NL_ST_MIN_CTAS
+#define NL_ST_MIN_CTAS 1
+#endif
+constexpr int ST_MIN_CTAS = NL_ST_MIN_CTAS;            // 2: a PDL successor's CTAs can co-reside and prefetch weights during this kernel's tail
 constexpr int ST_RED = 48;                            // max (rows per tile) * (warps per row)
 
 enum { ACT_NONE = 0, ACT_RMSNORM = 1 };
@@ -163,7 +167,7 @@ __device__ __forceinline__ float warp_fold(const float (&p)[RPT], int lane) {
 }
 
 template <int TYPE, int NM, int RPT, int ACT>
-__global__ void __launch_bounds__(ST_THREADS, 1) gemv_stream_kernel(const StreamArgs a) {
+__global__ void __launch_bounds__(ST_THREADS, ST_MIN_CTAS) gemv_stream_kernel(const StreamArgs a) {
     constexpr int QB = BlkBytes<TYPE>::Q, DB = BlkBytes<TYPE>::D;
     extern __shared__ __align__(128) uint8_t smem[];
     __shared__ uint64_t full_bar[ST_MAX_STAGES], empty_bar[ST_MAX_STAGES];

@@ -22,6 +22,7 @@ def main():
 
     cases = [("tiny_mha_qknorm_q8_0", G.load_gguf(os.path.join(ROOT, "tests", "golden", "tiny_mha_qknorm_q8_0.gguf")), 40),
              ("goldie-4L-q4_0", T.SyntheticGGUF("goldie", G.GGML_Q4_0, seed=2, seq_len=128, layers=4, vocab=4096), 24)]
+    cases.append(("big-2L-q4_0", T.SyntheticGGUF("big", G.GGML_Q4_0, seed=4, seq_len=64, layers=2, vocab=4096), 8))
     if world <= 4:
         cases.append(("large-2L-q8_0", T.SyntheticGGUF("large", G.GGML_Q8_0, seed=3, seq_len=64, layers=2, vocab=4096), 8))
     ok = True
