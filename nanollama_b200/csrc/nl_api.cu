@@ -15,6 +15,7 @@
 #include "nl_mega.cuh"
 #include "nl_tp.cuh"
 #include "nl_gemm.cuh"
+#include "nl_prefill.cuh"
 
 namespace nl {
 
@@ -256,6 +257,8 @@ struct nl_model {
     float *partial = nullptr, *logits_local = nullptr;
     uint8_t *tp_win = nullptr; TpLayout tp_lay{}; TpPeers tp_peers{}; bool tp_ready = false;
     unsigned int *d_ar_epoch = nullptr, *d_lg_epoch = nullptr;
+    // one-pass prefill workspace (allocated on first use, sized for seq_len rows)
+    float *pf_x = nullptr, *pf_qkv = nullptr, *pf_g = nullptr, *pf_u = nullptr; __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr; int pf_cap = 0;
     DevMat lm_view;   // this rank's vocab rows of the LM head (a view into output / tok_embd when tied; never freed)
     // per-token persistent kernel (batch 1)
     bool mega_ok = false;
@@ -776,6 +779,7 @@ void nl_destroy(nl_model *m) {
         if (m->d_lg_epoch) cudaFree(m->d_lg_epoch);
     }
     if (m->d_trace) cudaFree(m->d_trace);
+    if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     if (m->d_phases) cudaFree(m->d_phases);
     if (m->d_bar) cudaFree(m->d_bar);
     if (m->part_acc) cudaFree(m->part_acc);
@@ -849,12 +853,73 @@ static int prefill_sequential(nl_model *m, const int32_t *tokens, int n, int pos
     return NL_OK;
 }
 
+// One-pass prefill on the tensor cores: every projection of the T prompt tokens is ONE tcgen05 GEMM (nl_gemm.cuh) instead of T GEMVs.
+static bool prefill_gemm_ok(const nl_model *m, int n) {
+    if (getenv("NL_NO_GEMM_PREFILL") || n < 16 || m->tp > 1 || m->hd != 64) return false;
+    for (const Layer &ly : m->L)
+        for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown})
+            if (!gemm_eligible(*w)) return false;
+    return true;
+}
+static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
+    const nl_config &c = m->c;
+    const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, S = c.seq_len, ld = qdim + 2 * kvd;
+    cudaStream_t st = m->st;
+    if (!m->pf_cap) {
+        const size_t T = (size_t)S;
+        size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
+        NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4)); NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
+        NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
+        NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
+        m->pf_cap = S;
+    }
+    NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
+    NL_CUDA(cudaStreamSynchronize(st));   // tokens is caller memory
+    {
+        dim3 grid((dim + 255) / 256, n);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_prompt, m->gamma, m->gamma_map, m->pf_x, dim, 1, 0);
+    }
+    int rc;
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        if ((rc = gemm_run(ly.wq, m->pf_hi, m->pf_lo, n, ly.bq, m->pf_qkv, ld, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wk, m->pf_hi, m->pf_lo, n, ly.bk, m->pf_qkv + qdim, ld, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wv, m->pf_hi, m->pf_lo, n, ly.bv, m->pf_qkv + qdim + kvd, ld, GEPI_STORE, st))) return rc;
+        PrefillAttn a;
+        a.qkv = m->pf_qkv; a.ld = ld; a.T = n; a.pos0 = pos0;
+        a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
+        a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.out_hi = m->pf_hi; a.out_lo = m->pf_lo;
+        a.n_heads = m->nH; a.n_kv_heads = m->nKV; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate; a.eps = c.rms_norm_eps;
+        a.scale = (float)(1.0 / sqrt((double)m->hd));
+        rope_kv_kernel<<<n, 256, 0, st>>>(a);
+        attn_prefill_kernel<<<dim3(m->nH, (n + 31) / 32), 256, 0, st>>>(a);
+        if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st))) return rc;
+        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        if ((rc = gemm_run(ly.wgate, m->pf_hi, m->pf_lo, n, nullptr, m->pf_g, ffn, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wup, m->pf_hi, m->pf_lo, n, nullptr, m->pf_u, ffn, GEPI_STORE, st))) return rc;
+        {
+            const int64_t ne = (int64_t)n * ffn;
+            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
+        }
+        if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, m->pf_x, dim, GEPI_RESID, st))) return rc;
+    }
+    // the reference computes the LM head at every prompt position and uses only the last (go/main.go:160-166): last row only
+    NL_CUDA(cudaMemcpyAsync(m->x, m->pf_x + (size_t)(n - 1) * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, st));
+    const DevMat &out = m->output.present() ? m->output : m->tok_embd;
+    MatRef r = {&out, nullptr, nullptr, m->logits, c.vocab_size};
+    rc = gemv_dispatch(&r, 1, m->x, dim, 1, EPI_STORE, m->output_norm, c.rms_norm_eps, m->xb, m->opts, st, nullptr);
+    if (rc) return rc;
+    NL_CUDA(cudaGetLastError());
+    return NL_OK;
+}
+
 int nl_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *logits_last) {
     int rc = ready(m); if (rc) return rc;
     if (!tokens || n <= 0) return fail(NL_ERR_INVALID, "empty prompt");
     if (pos0 < 0 || pos0 + n > m->c.seq_len) return fail(NL_ERR_INVALID, "positions [%d,%d) exceed seq_len %d", pos0, pos0 + n, m->c.seq_len);
     for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m->c.vocab_size) return fail(NL_ERR_INVALID, "token %d out of range", tokens[i]);
-    rc = prefill_sequential(m, tokens, n, pos0); if (rc) return rc;
+    rc = prefill_gemm_ok(m, n) ? prefill_gemm(m, tokens, n, pos0) : prefill_sequential(m, tokens, n, pos0); if (rc) return rc;
     if (logits_last) NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));
     if (logits_last) memcpy(logits_last, m->h_logits, (size_t)m->c.vocab_size * 4);

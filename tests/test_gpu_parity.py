@@ -317,3 +317,60 @@ def test_tensor_parallel_2gpu_parity():
     r = subprocess.run([sys.executable, "-m", "torch.distributed.run", "--nnodes=1", "--nproc-per-node=2", "--master-addr", "127.0.0.1",
                         "--master-port", str(port), os.path.join(root, "tests", "tp_worker.py")], capture_output=True, text=True, timeout=900)
     assert r.returncode == 0 and "TP_PARITY_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
+# ---------------------------------------------------------------- prefill: tcgen05 GEMM path
+@pytest.mark.parametrize("typ", [G.GGML_Q4_0, G.GGML_Q8_0, G.GGML_F16])
+@pytest.mark.parametrize("rows,cols,batch", [(128, 64, 16), (1000, 768, 200), (2048, 1536, 384)])
+def test_matmul_many_rows_tensor_core_path(typ, rows, cols, batch):
+    """matmulDispatch with >= 16 activation rows runs as one tcgen05 GEMM (split-bf16, fp32 accumulate in TMEM)."""
+    rng = np.random.default_rng(rows + cols + batch + typ)
+    raw = G.encode_tensor((rng.standard_normal((rows, cols)) / np.sqrt(cols)).astype(np.float32), typ)
+    x = rng.standard_normal((batch, cols)).astype(np.float32)
+    got = M.DeviceMatrix(raw, typ, rows, cols).matmul(x)
+    for b in (0, 1, batch // 2, batch - 1):
+        assert maxrel(got[b], O.matmul(raw, typ, x[b], rows, cols)) < 1e-4   # observed ~8e-6 (dropped lo*lo term ~2^-17)
+
+
+@pytest.mark.parametrize("name", ["tiny_gqa_q4_0", "tiny_gqa_q8_0", "tiny_gqa_f16", "tiny_mha_qknorm_q8_0"])
+def test_prefill_one_pass_vs_token_by_token(golden_dir, gold, name):
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    toks = np.resize(gold["tokens"], 40)            # 40 prompt tokens -> the GEMM path (>= 16)
+    for pos, t in enumerate(toks):
+        exp = o.forward(int(t), pos)
+    m.reset()
+    m.prefill(toks)
+    assert maxrel(m.state.logits, exp) < LOGIT_TOL
+    assert maxrel(m.state.logits, exp) < 1e-4
+    # the KV cache written by the one-pass prefill must carry on into per-token decode
+    nxt = int(np.argmax(exp))
+    m.forward(nxt, len(toks))
+    assert maxrel(m.state.logits, o.forward(nxt, len(toks))) < 1e-4
+    # and a prefill that starts at a non-zero position (chunked prompt) sees the earlier chunk
+    m.reset(); o.reset()
+    m.prefill(toks[:20]); m.prefill(toks[20:], pos0=20)
+    for pos, t in enumerate(toks):
+        exp = o.forward(int(t), pos)
+    assert maxrel(m.state.logits, exp) < 1e-4
+    m.close()
+
+
+def test_prefill_mini_tier_512_tokens():
+    """BASELINE config 2: mini Q4_0, 512-token prefill (oracle checked on a 96-token prefix to keep the CPU side short)."""
+    gf = T.SyntheticGGUF("mini", G.GGML_Q4_0, seed=1, seq_len=1024)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(3)
+    toks = np.concatenate([[1], rng.integers(3, gf.meta.vocab_size, size=511)]).astype(np.int32)
+    for pos in range(96):
+        exp = o.forward(int(toks[pos]), pos)
+    m.prefill(toks[:96])
+    assert maxrel(m.state.logits, exp) < LOGIT_TOL
+    m.reset()
+    m.prefill(toks)                                   # full 512: determinism + finite
+    a = m.state.logits.copy()
+    m.reset(); m.prefill(toks)
+    assert np.array_equal(a, m.state.logits) and np.isfinite(a).all()
+    m.close()
