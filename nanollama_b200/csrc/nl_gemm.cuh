@@ -22,8 +22,9 @@ namespace nl {
 constexpr int GM_BM = 128, GM_BN = 128, GM_BK = 64;
 constexpr int GM_THREADS = 256;
 constexpr int GM_TILE_BYTES = GM_BM * GM_BK * 2;             // one bf16 operand tile: 16 KB
-constexpr int GM_STAGE_BYTES = 4 * GM_TILE_BYTES;            // a_hi, a_lo, w_hi, w_lo
+constexpr int GM_MAX_MT = 2;                                 // M tiles (128 rows each) per CTA sharing one dequantised W tile
 constexpr int GM_STAGES = 2;
+__host__ __device__ constexpr int gm_stage_bytes(int mt) { return (2 * mt + 2) * GM_TILE_BYTES; }   // mt x (a_hi, a_lo), w_hi, w_lo
 constexpr int GM_LBO = (GM_BM / 8) * 128;                    // bytes between core matrices adjacent in K   (2048)
 constexpr int GM_SBO = 128;                                  // bytes between core matrices adjacent in M/N
 
@@ -56,30 +57,32 @@ __device__ __forceinline__ void umma_commit(uint64_t *bar) {
 
 // split an fp32 pair into packed bf16 hi and the exact-remainder lo
 __device__ __forceinline__ void split2(float x, float y, uint32_t &hi, uint32_t &lo) {
-    const __nv_bfloat16 hx = __float2bfloat16_rn(x), hy = __float2bfloat16_rn(y);
-    const __nv_bfloat16 lx = __float2bfloat16_rn(x - __bfloat162float(hx)), ly = __float2bfloat16_rn(y - __bfloat162float(hy));
-    hi = (uint32_t)__bfloat16_as_ushort(hx) | ((uint32_t)__bfloat16_as_ushort(hy) << 16);
-    lo = (uint32_t)__bfloat16_as_ushort(lx) | ((uint32_t)__bfloat16_as_ushort(ly) << 16);
+    const __nv_bfloat162 h = __floats2bfloat162_rn(x, y);          // one packed conversion
+    hi = *reinterpret_cast<const uint32_t *>(&h);
+    const float fx = __uint_as_float(hi << 16), fy = __uint_as_float(hi & 0xFFFF0000u);   // bf16 -> fp32 is a shift
+    const __nv_bfloat162 l = __floats2bfloat162_rn(x - fx, y - fy);
+    lo = *reinterpret_cast<const uint32_t *>(&l);
 }
 
 // byte offset of the 16-byte chunk (row r, k-chunk kc) inside an operand tile
 __device__ __forceinline__ uint32_t tile_off(int r, int kc) { return (uint32_t)kc * GM_LBO + (uint32_t)(r >> 3) * GM_SBO + (uint32_t)(r & 7) * 16; }
 
-template <int TYPE>
+template <int TYPE, int MT>
 __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g) {
+    constexpr int STAGE_BYTES = gm_stage_bytes(MT);
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mma_bar[GM_STAGES];
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
-    const int n0 = blockIdx.x * GM_BN, m0 = blockIdx.y * GM_BM;
+    const int n0 = blockIdx.x * GM_BN, m0 = blockIdx.y * GM_BM * MT;
     const int nb = g.K / 32;
 
     if (tid == 0) {
         for (int s = 0; s < GM_STAGES; s++) mbar_init(&mma_bar[s], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    if (warp == 0) {  // 128 TMEM columns: the fp32 128x128 accumulator
-        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], 128;" ::"r"(smem_u32(&tmem_base_s)) : "memory");
+    if (warp == 0) {  // 128 TMEM columns per fp32 128x128 accumulator
+        asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(&tmem_base_s)), "n"(128 * MT) : "memory");
         asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
@@ -88,82 +91,106 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g
     const uint32_t tmem_c = tmem_base_s;
 
     const int ksteps = g.K / GM_BK;
+    // raw operands of one K step, fetched one step ahead so that the global-load latency hides behind the conversion of the
+    // previous step and the MMAs in flight
+    struct Raw { uint4 wq[4]; float d; };
+    const int wn = tid & 127, wb = tid >> 7;            // W: my row inside the tile and my quant block inside the K step
+    const bool w_ok = n0 + wn < g.N;
+    auto fetch = [&](int ks, Raw &r) {
+        const int k0 = ks * GM_BK;
+        r.d = 0.f;
+#pragma unroll
+        for (int i = 0; i < 4; i++) r.wq[i] = make_uint4(0, 0, 0, 0);
+        if (w_ok) {
+            if constexpr (TYPE == NL_Q4_0) {
+                const size_t bi = (size_t)(n0 + wn) * nb + (k0 >> 5) + wb;
+                r.wq[0] = ldg_stream_u4(g.qs + bi * 16);
+                r.d = __half2float(g.d[bi]);
+            } else if constexpr (TYPE == NL_Q8_0) {
+                const size_t bi = (size_t)(n0 + wn) * nb + (k0 >> 5) + wb;
+                r.wq[0] = ldg_stream_u4(g.qs + bi * 32);
+                r.wq[1] = ldg_stream_u4(g.qs + bi * 32 + 16);
+                r.d = __half2float(g.d[bi]);
+            } else {
+                const __half *wp = reinterpret_cast<const __half *>(g.qs) + (size_t)(n0 + wn) * g.K + k0 + 32 * wb;
+#pragma unroll
+                for (int i = 0; i < 4; i++) r.wq[i] = ldg_stream_u4(wp + 8 * i);
+            }
+        }
+    };
+    Raw cur;
+    fetch(0, cur);
     for (int ks = 0; ks < ksteps; ks++) {
         const int s = ks & 1;
+        Raw nxt;
+        if (ks + 1 < ksteps) fetch(ks + 1, nxt);
         if (ks >= GM_STAGES) mbar_wait(&mma_bar[s], ((ks >> 1) - 1) & 1);  // the MMAs that read this stage have completed
-        uint8_t *st = smem + (size_t)s * GM_STAGE_BYTES;
-        uint8_t *a_hi = st, *a_lo = st + GM_TILE_BYTES, *w_hi = st + 2 * GM_TILE_BYTES, *w_lo = st + 3 * GM_TILE_BYTES;
-        const int k0 = ks * GM_BK;
-        // ---- A: 128 rows x 8 chunks of 8 bf16, two planes, straight copy (rows beyond T are zero)
+        uint8_t *st = smem + (size_t)s * STAGE_BYTES;
+        uint8_t *w_hi = st + 2 * MT * GM_TILE_BYTES, *w_lo = w_hi + GM_TILE_BYTES;
+        // ---- A: MT x 128 rows x 8 chunks of 8 bf16, two planes each: cp.async straight into the UMMA layout (rows >= T: zeros);
+        //      the copies land while this thread dequantises its share of W below
+        {
+            const int k0 = ks * GM_BK;
 #pragma unroll
-        for (int j = 0; j < 4; j++) {
-            const int q = tid + GM_THREADS * j, row = q & 127, kc = q >> 7;
-            uint4 vh = make_uint4(0, 0, 0, 0), vl = make_uint4(0, 0, 0, 0);
-            if (m0 + row < g.T) {
-                const size_t off = (size_t)(m0 + row) * g.K + k0 + kc * 8;
-                vh = *reinterpret_cast<const uint4 *>(g.a_hi + off);
-                vl = *reinterpret_cast<const uint4 *>(g.a_lo + off);
+            for (int j = 0; j < 4 * MT; j++) {
+                const int q = tid + GM_THREADS * j, row = q & (128 * MT - 1), kc = q / (128 * MT), mt = row >> 7, r = row & 127;
+                uint8_t *dh = st + (2 * mt) * GM_TILE_BYTES + tile_off(r, kc), *dl = dh + GM_TILE_BYTES;
+                if (m0 + row < g.T) {
+                    const size_t off = (size_t)(m0 + row) * g.K + k0 + kc * 8;
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dh)), "l"(g.a_hi + off) : "memory");
+                    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dl)), "l"(g.a_lo + off) : "memory");
+                } else {
+                    *reinterpret_cast<uint4 *>(dh) = make_uint4(0, 0, 0, 0);
+                    *reinterpret_cast<uint4 *>(dl) = make_uint4(0, 0, 0, 0);
+                }
             }
-            *reinterpret_cast<uint4 *>(a_hi + tile_off(row, kc)) = vh;
-            *reinterpret_cast<uint4 *>(a_lo + tile_off(row, kc)) = vl;
+            asm volatile("cp.async.commit_group;" ::: "memory");
         }
         // ---- W: thread = (row n, quant block b of this K step); dequantise 32 weights, split, store 4 chunks per plane
         {
-            const int n = tid & 127, b = tid >> 7;
             float w[32];
-            if (n0 + n < g.N) {
-                if constexpr (TYPE == NL_Q4_0) {
-                    const size_t bi = (size_t)(n0 + n) * nb + (k0 >> 5) + b;
-                    const uint4 q = ldg_stream_u4(g.qs + bi * 16);
-                    const float d = __half2float(g.d[bi]);
-                    const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
+            if constexpr (TYPE == NL_Q4_0) {
+                const uint32_t ws[4] = {cur.wq[0].x, cur.wq[0].y, cur.wq[0].z, cur.wq[0].w};
+#pragma unroll
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t lo4 = ws[i] & 0x0F0F0F0Fu, hi4 = (ws[i] >> 4) & 0x0F0F0F0Fu;
+#pragma unroll
+                    for (int k = 0; k < 4; k++) {   // exact int -> fp32 without I2F: 0x4B000000 | n is 2^23 + n
+                        w[4 * i + k] = (u8_to_f32_magic(lo4, k) - 8388616.0f) * cur.d;
+                        w[4 * i + k + 16] = (u8_to_f32_magic(hi4, k) - 8388616.0f) * cur.d;
+                    }
+                }
+            } else if constexpr (TYPE == NL_Q8_0) {
+#pragma unroll
+                for (int h = 0; h < 2; h++) {
+                    const uint32_t ws[4] = {cur.wq[h].x ^ 0x80808080u, cur.wq[h].y ^ 0x80808080u, cur.wq[h].z ^ 0x80808080u, cur.wq[h].w ^ 0x80808080u};
 #pragma unroll
                     for (int i = 0; i < 4; i++)
 #pragma unroll
-                        for (int k = 0; k < 4; k++) {
-                            const uint32_t byte = (ws[i] >> (8 * k)) & 0xFF;
-                            w[4 * i + k] = (float)((int)(byte & 0x0F) - 8) * d;
-                            w[4 * i + k + 16] = (float)((int)(byte >> 4) - 8) * d;
-                        }
-                } else if constexpr (TYPE == NL_Q8_0) {
-                    const size_t bi = (size_t)(n0 + n) * nb + (k0 >> 5) + b;
-                    const float d = __half2float(g.d[bi]);
-#pragma unroll
-                    for (int h = 0; h < 2; h++) {
-                        const uint4 q = ldg_stream_u4(g.qs + bi * 32 + 16 * h);
-                        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++)
-#pragma unroll
-                            for (int k = 0; k < 4; k++) w[16 * h + 4 * i + k] = (float)(int8_t)((ws[i] >> (8 * k)) & 0xFF) * d;
-                    }
-                } else {  // F16 rows
-                    const __half *wp = reinterpret_cast<const __half *>(g.qs) + (size_t)(n0 + n) * g.K + k0 + 32 * b;
-#pragma unroll
-                    for (int h = 0; h < 4; h++) {
-                        const uint4 q = ldg_stream_u4(wp + 8 * h);
-                        const uint32_t ws[4] = {q.x, q.y, q.z, q.w};
-#pragma unroll
-                        for (int i = 0; i < 4; i++) {
-                            const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&ws[i]));
-                            w[8 * h + 2 * i] = f.x; w[8 * h + 2 * i + 1] = f.y;
-                        }
-                    }
+                        for (int k = 0; k < 4; k++) w[16 * h + 4 * i + k] = (u8_to_f32_magic(ws[i], k) - 8388736.0f) * cur.d;
                 }
             } else {
 #pragma unroll
-                for (int i = 0; i < 32; i++) w[i] = 0.f;
+                for (int h = 0; h < 4; h++) {
+                    const uint32_t ws[4] = {cur.wq[h].x, cur.wq[h].y, cur.wq[h].z, cur.wq[h].w};
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const float2 f = __half22float2(*reinterpret_cast<const __half2 *>(&ws[i]));
+                        w[8 * h + 2 * i] = f.x; w[8 * h + 2 * i + 1] = f.y;
+                    }
+                }
             }
 #pragma unroll
             for (int c = 0; c < 4; c++) {
                 uint4 vh, vl;
                 split2(w[8 * c + 0], w[8 * c + 1], vh.x, vl.x); split2(w[8 * c + 2], w[8 * c + 3], vh.y, vl.y);
                 split2(w[8 * c + 4], w[8 * c + 5], vh.z, vl.z); split2(w[8 * c + 6], w[8 * c + 7], vh.w, vl.w);
-                const uint32_t off = tile_off(n, b * 4 + c);
+                const uint32_t off = tile_off(wn, wb * 4 + c);
                 *reinterpret_cast<uint4 *>(w_hi + off) = vh;
                 *reinterpret_cast<uint4 *>(w_lo + off) = vl;
             }
         }
+        asm volatile("cp.async.wait_all;" ::: "memory");
         asm volatile("fence.proxy.async.shared::cta;" ::: "memory");  // generic-proxy stores -> visible to the tensor core (async proxy)
         __syncthreads();
         if (tid == 0) {
@@ -172,14 +199,20 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g
 #pragma unroll
             for (int kk = 0; kk < GM_BK / 16; kk++) {   // one MMA consumes K=16 = two core matrices along K
                 const uint32_t koff = kk * 2 * GM_LBO;
-                const uint64_t ah = umma_desc(smem_u32(a_hi) + koff, lbo, sbo), al = umma_desc(smem_u32(a_lo) + koff, lbo, sbo);
                 const uint64_t wh = umma_desc(smem_u32(w_hi) + koff, lbo, sbo), wl = umma_desc(smem_u32(w_lo) + koff, lbo, sbo);
-                umma_f16(tmem_c, ah, wh, GM_IDESC, (ks | kk) != 0);
-                umma_f16(tmem_c, ah, wl, GM_IDESC, 1);
-                umma_f16(tmem_c, al, wh, GM_IDESC, 1);
+#pragma unroll
+                for (int mt = 0; mt < MT; mt++) {
+                    const uint32_t a_hi = smem_u32(st + (2 * mt) * GM_TILE_BYTES), a_lo = a_hi + GM_TILE_BYTES;
+                    const uint64_t ah = umma_desc(a_hi + koff, lbo, sbo), al = umma_desc(a_lo + koff, lbo, sbo);
+                    const uint32_t acc = tmem_c + mt * 128;   // accumulator mt lives in TMEM columns [128 mt, 128 mt + 128)
+                    umma_f16(acc, ah, wh, GM_IDESC, (ks | kk) != 0);
+                    umma_f16(acc, ah, wl, GM_IDESC, 1);
+                    umma_f16(acc, al, wh, GM_IDESC, 1);
+                }
             }
             umma_commit(&mma_bar[s]);   // arrives when every MMA issued so far has finished (implies fence::before_thread_sync)
         }
+        cur = nxt;
     }
     // ---- epilogue: wait for the last commit (it covers all earlier MMAs), TMEM -> registers -> global
     {
@@ -187,12 +220,13 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g
         mbar_wait(&mma_bar[last & 1], (last >> 1) & 1);
         asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
         const int lg = warp & 3, ch = warp >> 2;           // TMEM lane group of this warp, column half
-        const int row = m0 + lg * 32 + lane;
 #pragma unroll
-        for (int cc = 0; cc < 2; cc++) {
+        for (int mc = 0; mc < 2 * MT; mc++) {
+            const int mt = mc >> 1, cc = mc & 1;
+            const int row = m0 + mt * 128 + lg * 32 + lane;
             const int col0 = ch * 64 + cc * 32;
             uint32_t r[32];
-            const uint32_t taddr = tmem_c + ((uint32_t)(lg * 32) << 16) + (uint32_t)col0;
+            const uint32_t taddr = tmem_c + ((uint32_t)(lg * 32) << 16) + (uint32_t)(mt * 128 + col0);
             asm volatile(
                 "tcgen05.ld.sync.aligned.32x32b.x32.b32 {%0,%1,%2,%3,%4,%5,%6,%7,%8,%9,%10,%11,%12,%13,%14,%15,%16,%17,%18,%19,%20,%21,%22,%23,%24,%25,%26,%27,"
                 "%28,%29,%30,%31}, [%32];"
@@ -218,7 +252,7 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g
     }
     asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory");
     __syncthreads();
-    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, 128;" ::"r"(tmem_c) : "memory");
+    if (warp == 0) asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(tmem_c), "n"(128 * MT) : "memory");
 }
 
 // fp32 [n] -> bf16 hi / lo planes (exact two-term split up to 16 bits)
@@ -235,18 +269,23 @@ static __global__ void split_bf16_kernel(const float *__restrict__ x, __nv_bfloa
     }
 }
 
-template <int TYPE>
-int launch_gemm_typed(const GemmArgs &g, cudaStream_t st) {
+template <int TYPE, int MT>
+static int launch_gemm_mt(const GemmArgs &g, cudaStream_t st) {
     static bool configured = false;
-    auto kern = gemm_tc_kernel<TYPE>;
-    const size_t smem = (size_t)GM_STAGES * GM_STAGE_BYTES;
+    auto kern = gemm_tc_kernel<TYPE, MT>;
+    const size_t smem = (size_t)GM_STAGES * gm_stage_bytes(MT);
     if (!configured) {
         if (cudaFuncSetAttribute(kern, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem) != cudaSuccess) return -2;
         configured = true;
     }
-    dim3 grid((g.N + GM_BN - 1) / GM_BN, (g.T + GM_BM - 1) / GM_BM);
+    dim3 grid((g.N + GM_BN - 1) / GM_BN, (g.T + GM_BM * MT - 1) / (GM_BM * MT));
     kern<<<grid, GM_THREADS, smem, st>>>(g);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
+}
+template <int TYPE>
+int launch_gemm_typed(const GemmArgs &g, cudaStream_t st) {
+    // two 128-token tiles per CTA share one dequantised W tile once there are enough tokens to fill them
+    return g.T > GM_BM ? launch_gemm_mt<TYPE, 2>(g, st) : launch_gemm_mt<TYPE, 1>(g, st);
 }
 int launch_gemm_q4_0(const GemmArgs &g, cudaStream_t st);
 int launch_gemm_q8_0(const GemmArgs &g, cudaStream_t st);

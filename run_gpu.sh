@@ -1,2 +1,3 @@
-timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"gemm_tc|attn_prefill|rope_kv|rmsnorm_split|swiglu_split|embed" -c 400 --csv --log-file gpurun_out/launches_prefill.csv python tools/prefill_bench.py --tier goldie --tokens 2047 --iters 1 > gpurun_out/ncu_prefill.log 2>&1; echo "ncu rc=$?"
-timeout 600 ncu --set full --clock-control none --import-source on -k regex:gemm_tc -s 40 -c 3 -o gpurun_out/prof_gemm python tools/prefill_bench.py --tier goldie --tokens 2047 --iters 1 > gpurun_out/ncu_gemm.log 2>&1; echo "ncu full rc=$?"
+timeout 900 python -m pytest tests -m gpu -q -x --timeout 300 -k "tensor_core or prefill" > gpurun_out/pytest_prefill.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_prefill.log
+timeout 300 python tools/prefill_bench.py --tier goldie --tokens 2047 2>&1 | tail -1
+timeout 300 python tools/prefill_bench.py --tier mini --tokens 512 2>&1 | tail -1
