@@ -182,6 +182,7 @@ def main():
     t0 = time.time()
     m = M.load_llama_model(gf, device=local_rank, tp_rank=rank if tp > 1 else 0, tp_size=tp)
     load_s = time.time() - t0
+    decode_path = m.decode_path
     rng = np.random.default_rng(5)
     prompt = np.concatenate([[1], rng.integers(3, gf.meta.vocab_size, size=PROMPT_LEN - 1)]).astype(np.int32)
 
@@ -260,7 +261,7 @@ def main():
     except Exception as e:  # never let the extra measurement kill the bench line
         alone = {"error": str(e)}
     roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
-                "peak_source": peak_src, "kernel": "gemv_stream_kernel (dequant-fused GEMV family)",
+                "peak_source": peak_src, "kernel": decode_path,
                 "bytes_per_step": int(bytes_tok), "gemv_share_of_bytes": weight_only / bytes_tok, "kernel_alone": alone,
                 "how": "algorithmic bytes per decode step / CUDA-event time per step (lower bound of the kernel's bandwidth); "
                        "kernel_alone = LM-head GEMV timed back to back on L2-cold replicas"}

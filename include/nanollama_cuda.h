@@ -141,6 +141,9 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
 int nl_launches_per_token(const nl_model *m);
 /* bytes of weights resident on this device (after sharding) */
 int64_t nl_weight_bytes(const nl_model *m);
+/* name of the kernel family that executes a batch-1 Forward of this model ("decode_tiled_kernel", "decode_mega_kernel",
+ * "gemv_stream_kernel chain"); static string */
+const char *nl_decode_path(const nl_model *m);
 
 /* ---- tensor-parallel plumbing (tp_size > 1): peers exchange 64-byte CUDA IPC handles of their all-reduce windows
  * through the host's process group (torch.distributed in the Python host), then hand them back here. ---- */

@@ -13,6 +13,7 @@
 #include "nl_kernels.cuh"
 #include "nl_stream.cuh"
 #include "nl_mega.cuh"
+#include "nl_tile.cuh"
 #include "nl_tp.cuh"
 #include "nl_gemm.cuh"
 #include "nl_prefill.cuh"
@@ -266,6 +267,12 @@ struct nl_model {
     MegaArgs margs; int mega_grid = 0; size_t mega_smem = 0; int mega_type = -1;
     unsigned long long *d_trace = nullptr;
     int mega_reps = 1;
+    // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
+    bool tile_ok = false;
+    std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
+    float *qkv = nullptr;               // [qdim + 2 kvd] contiguous q | k | v of the tiled path
+    float *qkv_bias = nullptr;
+    TilePhase *d_tphases = nullptr; TileArgs targs; int tile_grid = 0;
     int act_stride = 0;          // floats between the MG_REPS copies of x / xb2 / hb (replica 0 is what every other path uses)
     float *attn_out = nullptr;   // xb2 with replicas
 };
@@ -393,6 +400,123 @@ static int build_mega(nl_model *m) {
     return NL_OK;
 }
 
+// ---- tiled tensor-core decode path (nl_tile.cuh) ----
+static bool tile_eligible(const DevMat &w) {
+    return w.type == NL_Q4_0 && w.rows % 16 == 0 && w.cols % 32 == 0 && w.cols <= (int64_t)TL_MAX_NBG * 128 && w.rows * (w.cols / 32) < (1ll << 31);
+}
+// Builds one tiled matrix from `n` planar matrices of equal cols: concatenated row-wise (interleave = false) or with their
+// 16-row groups interleaved (gate/up: group i of mats[0], group i of mats[1], ...).
+static int make_tiles(uint8_t **dst, const DevMat *const *mats, int n, bool interleave, cudaStream_t st) {
+    const int nb = (int)(mats[0]->cols / 32), nbg = (nb + 3) / 4;
+    int64_t n_rg = 0;
+    for (int i = 0; i < n; i++) n_rg += mats[i]->rows / 16;
+    NL_CUDA(cudaMalloc(dst, (size_t)n_rg * nbg * TL_TILE));
+    int off = 0;
+    for (int i = 0; i < n; i++) {
+        const DevMat &w = *mats[i];
+        if (launch_tile_q4_0(w.qs, w.d, (int)w.rows, nb, *dst, nbg, interleave ? i : off, interleave ? n : 1, st)) return fail(NL_ERR_CUDA, "tile repack launch failed");
+        off += (int)(w.rows / 16);
+    }
+    return NL_OK;
+}
+static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const float *x, const float *norm_w,
+                            const float *bias, float *out) {
+    memset(&P, 0, sizeof P);
+    P.kind = PH_GEMV; P.tiles = tiles; P.n_rg = n_rg; P.nbg = (cols / 32 + 3) / 4; P.nbg_magic = tile_magic(P.nbg); P.unit_rg = unit_rg;
+    P.cols = cols; P.rows = rows; P.epi = epi; P.x = x; P.norm_w = norm_w; P.bias = bias; P.out = out;
+}
+
+// Phase list of the tiled persistent kernel.  Leaves tile_ok = false when the model does not fit (types other than Q4_0, rows not a
+// multiple of 16, head_dim != 64, tensor parallel ...): the per-matrix kernels are used then.
+static int build_tiled(nl_model *m) {
+    const nl_config &c = m->c;
+    m->tile_ok = false;
+    if (getenv("NL_NO_TILED") || getenv("NL_MEGA") || m->tp > 1) return NL_OK;
+    if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
+    const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
+    if (!tile_eligible(outw)) return NL_OK;
+    bool any_bias = false;
+    for (const Layer &ly : m->L) {
+        for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown}) if (!tile_eligible(*w)) return NL_OK;
+        if (ly.bq || ly.bk || ly.bv) any_bias = true;
+    }
+    const int G = m->opts.num_sms;
+    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size, nqkv = qdim + 2 * kvd;
+    cudaStream_t st = m->st;
+    NL_CUDA(cudaMalloc(&m->qkv, (size_t)nqkv * 4));
+    NL_CUDA(cudaMemset(m->qkv, 0, (size_t)nqkv * 4));
+    if (any_bias) {   // q | k | v biases in the same order as the concatenated rows (absent ones are zero)
+        NL_CUDA(cudaMalloc(&m->qkv_bias, (size_t)c.n_layers * nqkv * 4));
+        NL_CUDA(cudaMemset(m->qkv_bias, 0, (size_t)c.n_layers * nqkv * 4));
+        for (int l = 0; l < c.n_layers; l++) {
+            float *b = m->qkv_bias + (size_t)l * nqkv;
+            const Layer &ly = m->L[l];
+            if (ly.bq) NL_CUDA(cudaMemcpyAsync(b, ly.bq, (size_t)qdim * 4, cudaMemcpyDeviceToDevice, st));
+            if (ly.bk) NL_CUDA(cudaMemcpyAsync(b + qdim, ly.bk, (size_t)kvd * 4, cudaMemcpyDeviceToDevice, st));
+            if (ly.bv) NL_CUDA(cudaMemcpyAsync(b + qdim + kvd, ly.bv, (size_t)kvd * 4, cudaMemcpyDeviceToDevice, st));
+        }
+    }
+    std::vector<TilePhase> ph;
+    TilePhase P;
+    int rc;
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        uint8_t *t_qkv = nullptr, *t_o = nullptr, *t_gu = nullptr, *t_dn = nullptr;
+        const DevMat *qkv[3] = {&ly.wq, &ly.wk, &ly.wv}, *o[1] = {&ly.wo}, *gu[2] = {&ly.wgate, &ly.wup}, *dn[1] = {&ly.wdown};
+        if ((rc = make_tiles(&t_qkv, qkv, 3, false, st))) return rc;
+        m->tile_bufs.push_back(t_qkv);
+        if ((rc = make_tiles(&t_o, o, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t_o);
+        if ((rc = make_tiles(&t_gu, gu, 2, true, st))) return rc;
+        m->tile_bufs.push_back(t_gu);
+        if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t_dn);
+        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, m->x, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv);
+        ph.push_back(P);
+        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
+        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->xb2, nullptr, ly.bo, m->x);
+        ph.push_back(P);
+        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, m->x, ly.ffn_norm, nullptr, m->hb);
+        ph.push_back(P);
+        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb, nullptr, nullptr, m->x);
+        ph.push_back(P);
+    }
+    {
+        uint8_t *t_lm = nullptr;
+        const DevMat *lm[1] = {&outw};
+        if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t_lm);
+        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, m->x, m->output_norm, nullptr, m->logits);
+        ph.push_back(P);
+    }
+    NL_CUDA(cudaStreamSynchronize(st));
+    int nsplit = G / c.n_kv_heads;
+    if (nsplit < 1) nsplit = 1;
+    if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
+    NL_CUDA(cudaMalloc(&m->d_tphases, ph.size() * sizeof(TilePhase)));
+    NL_CUDA(cudaMemcpy(m->d_tphases, ph.data(), ph.size() * sizeof(TilePhase), cudaMemcpyHostToDevice));
+    const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
+    NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
+    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 4));
+    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
+    TileArgs &a = m->targs;
+    memset(&a, 0, sizeof a);
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps;
+    a.at.q = m->qkv; a.at.k = m->qkv + qdim; a.at.v = m->qkv + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
+    a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
+    a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
+    a.at.nsplit = nsplit; a.at.out = m->xb2; a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
+    a.at.scale = (float)(1.0 / sqrt((double)m->hd));
+    if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
+        NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
+        a.trace = m->d_trace;
+    }
+    m->tile_grid = G;
+    m->tile_ok = true;
+    return NL_OK;
+}
+
 // The launch sequence of one Forward for `batch` sequences (go/model.go:490-620).  Recorded into a CUDA graph.
 static int record_forward(nl_model *m, int batch) {
     const nl_config &c = m->c;
@@ -404,6 +528,15 @@ static int record_forward(nl_model *m, int batch) {
         dim3 grid((dim + 255) / 256, batch);
         embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim, (batch == 1 && m->mega_ok) ? m->mega_reps : 1, m->act_stride);
         launches++;
+    }
+    if (batch == 1 && m->tile_ok) {
+        // everything after the embedding in ONE persistent tensor-core kernel (nl_tile.cuh); its grid-barrier counters start at zero
+        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
+        if (launch_tiled(m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        launches++;
+        NL_CUDA(cudaGetLastError());
+        m->launches_fwd = launches;
+        return NL_OK;
     }
     if (batch == 1 && m->mega_ok) {
         // everything after the embedding in ONE persistent kernel (nl_mega.cuh); its grid-barrier counters start at zero
@@ -746,6 +879,8 @@ int nl_finalize(nl_model *m) {
         m->finalized = true;   // graphs are captured by nl_tp_import_handles once the peers' windows are mapped
         return NL_OK;
     }
+    rc = build_tiled(m);
+    if (rc) return rc;
     rc = build_mega(m);
     if (rc) return rc;
     rc = build_graphs(m, 1);
@@ -780,6 +915,10 @@ void nl_destroy(nl_model *m) {
     }
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
+    for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
+    if (m->qkv) cudaFree(m->qkv);
+    if (m->qkv_bias) cudaFree(m->qkv_bias);
+    if (m->d_tphases) cudaFree(m->d_tphases);
     if (m->d_phases) cudaFree(m->d_phases);
     if (m->d_bar) cudaFree(m->d_bar);
     if (m->part_acc) cudaFree(m->part_acc);
@@ -982,17 +1121,22 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
     NL_CUDA(cudaStreamSynchronize(m->st));
     NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
     if (m->d_trace && getenv("NL_TRACE")) {
-        size_t n = (size_t)m->mega_grid * m->margs.n_phases * 8;
+        const int tg = m->tile_ok ? m->tile_grid : m->mega_grid, tp_ = m->tile_ok ? m->targs.n_phases : m->margs.n_phases;
+        size_t n = (size_t)tg * tp_ * 8;
         std::vector<unsigned long long> h(n);
         NL_CUDA(cudaMemcpy(h.data(), m->d_trace, n * 8, cudaMemcpyDeviceToHost));
         FILE *f = fopen(getenv("NL_TRACE"), "wb");
-        if (f) { int hdr[2] = {m->mega_grid, m->margs.n_phases}; fwrite(hdr, 4, 2, f); fwrite(h.data(), 8, n, f); fclose(f); }
+        if (f) { int hdr[2] = {tg, tp_}; fwrite(hdr, 4, 2, f); fwrite(h.data(), 8, n, f); fclose(f); }
     }
     return NL_OK;
 }
 
 int nl_launches_per_token(const nl_model *m) { return m ? m->launches_fwd + 1 : 0; }
 int64_t nl_weight_bytes(const nl_model *m) { return m ? m->weight_bytes : 0; }
+const char *nl_decode_path(const nl_model *m) {
+    if (!m) return "";
+    return m->tile_ok ? "decode_tiled_kernel" : m->mega_ok ? "decode_mega_kernel" : "gemv_stream_kernel chain";
+}
 
 // ---- operator-level hooks ----
 int nl_dequant(uint32_t type, const void *host_src, int64_t n, float *host_dst) {
@@ -1030,7 +1174,40 @@ struct nl_matrix {
     __nv_bfloat16 *xh = nullptr, *xl = nullptr;   // bf16 planes of x for the tensor-core path
     cudaStream_t st = nullptr;
     GemvOpts opts{148, true, true};
+    // batch-1 Q4_0: fragment-tiled replicas + one-phase descriptors for the tensor-core GEMV (nl_tile.cuh)
+    std::vector<uint8_t *> tiles;
+    TilePhase *d_tph = nullptr; unsigned int *d_tbar = nullptr; int tph_cap = 0;
 };
+
+// tiled replica of copy `idx` (built on first use) and a one-phase descriptor per replica
+static int matrix_tiles(nl_matrix *w, int n_copies) {
+    const DevMat &m0 = w->copies[0];
+    if (getenv("NL_NO_TILED") || !tile_eligible(m0)) return 1;
+    while ((int)w->tiles.size() < n_copies) {
+        uint8_t *t = nullptr;
+        const DevMat *one[1] = {&w->copies[w->tiles.size()]};
+        int rc = make_tiles(&t, one, 1, false, w->st); if (rc) return rc;
+        w->tiles.push_back(t);
+    }
+    if (w->tph_cap < n_copies) {
+        if (w->d_tph) cudaFree(w->d_tph);
+        if (!w->d_tbar) { NL_CUDA(cudaMalloc(&w->d_tbar, 4)); NL_CUDA(cudaMemset(w->d_tbar, 0, 4)); }
+        std::vector<TilePhase> ph(n_copies);
+        for (int i = 0; i < n_copies; i++)
+            tile_gemv_phase(ph[i], w->tiles[i], (int)(m0.rows / 16), (int)m0.cols, 1, (int)m0.rows, TEPI_STORE, w->x, nullptr, nullptr, w->out);
+        NL_CUDA(cudaMalloc(&w->d_tph, n_copies * sizeof(TilePhase)));
+        NL_CUDA(cudaMemcpy(w->d_tph, ph.data(), n_copies * sizeof(TilePhase), cudaMemcpyHostToDevice));
+        w->tph_cap = n_copies;
+    }
+    return NL_OK;
+}
+static int matrix_tiled_gemv(nl_matrix *w, int idx) {
+    TileArgs a; memset(&a, 0, sizeof a);
+    a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar;
+    const int units = (int)(w->copies[0].rows / 16);
+    if (launch_tiled(a, units < w->opts.num_sms ? units : w->opts.num_sms, w->st)) return fail(NL_ERR_CUDA, "tiled gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    return NL_OK;
+}
 
 int nl_matrix_create(uint32_t type, const void *host_w, int64_t rows, int64_t cols, int32_t device, nl_matrix **out) {
     if (!host_w || !out) return fail(NL_ERR_INVALID, "null argument");
@@ -1051,6 +1228,7 @@ static int matrix_buffers(nl_matrix *w, int batch) {
     if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
     if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
     w->x = w->out = nullptr; w->xh = w->xl = nullptr;
+    w->tph_cap = 0;   // the one-phase descriptors point at x / out
     NL_CUDA(cudaMalloc(&w->xh, (size_t)batch * w->copies[0].cols * 2));
     NL_CUDA(cudaMalloc(&w->xl, (size_t)batch * w->copies[0].cols * 2));
     NL_CUDA(cudaMalloc(&w->x, (size_t)batch * w->copies[0].cols * 4));
@@ -1069,6 +1247,9 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
     if (batch >= gemm_min && gemm_eligible(m)) {   // many rows of x: the T-token GEMM on the tensor cores
         rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * m.cols, w->st); if (rc) return rc;
         rc = gemm_run(m, w->xh, w->xl, batch, nullptr, w->out, (int)m.rows, GEPI_STORE, w->st); if (rc) return rc;
+    } else if (batch == 1 && (rc = matrix_tiles(w, 1)) <= 0) {   // batch 1, Q4_0: the tensor-core GEMV of the decode path
+        if (rc) return rc;
+        rc = matrix_tiled_gemv(w, 0); if (rc) return rc;
     } else {
         if (batch > 64) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 64 == 0", batch);
         MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
@@ -1093,11 +1274,16 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     }
     NL_CUDA(cudaMemsetAsync(w->x, 0, (size_t)batch * src.cols * 4, w->st));
     cudaEvent_t e0, e1; NL_CUDA(cudaEventCreate(&e0)); NL_CUDA(cudaEventCreate(&e1));
+    const int tiled = batch == 1 ? matrix_tiles(w, n_copies) : 1;
+    if (tiled < 0) return tiled;
     int idx = 0;
     for (int i = 0; i < warmup + iters; i++) {
         if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));
-        MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
-        rc = gemv_dispatch(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
+        if (tiled == 0) { rc = matrix_tiled_gemv(w, idx); if (rc) return rc; }
+        else {
+            MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
+            rc = gemv_dispatch(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
+        }
         idx = (idx + 1) % n_copies;
     }
     NL_CUDA(cudaEventRecord(e1, w->st));
@@ -1113,6 +1299,9 @@ void nl_matrix_destroy(nl_matrix *w) {
     cudaSetDevice(w->device);
     if (w->st) cudaStreamSynchronize(w->st);
     for (auto &c : w->copies) free_mat(c);
+    for (uint8_t *t : w->tiles) if (t) cudaFree(t);
+    if (w->d_tph) cudaFree(w->d_tph);
+    if (w->d_tbar) cudaFree(w->d_tbar);
     if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
     if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
     if (w->st) cudaStreamDestroy(w->st);

@@ -195,7 +195,8 @@ __device__ __forceinline__ unsigned long long gtime() {
     return t;
 }
 #define MG_TRACE(p, k) do { if (A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
-__device__ __forceinline__ void mega_consumer_bar() { asm volatile("bar.sync 1, %0;" ::"n"(MG_CONSUMERS) : "memory"); }
+template <int NT> __device__ __forceinline__ void cons_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
+__device__ __forceinline__ void mega_consumer_bar() { cons_bar<MG_CONSUMERS>(); }
 
 // contiguous band of a phase's tiles for CTA b of G
 __device__ __forceinline__ void tile_band(int total, int b, int G, int &t0, int &t1) {
@@ -378,6 +379,7 @@ struct AttnSmem {
     int is_last;
 };
 
+template <int NT>
 __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int item, AttnSmem &S, int tid) {
     constexpr int HD = 64, HALF = 32;
     const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
@@ -392,7 +394,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
 
     // ---- RoPE (+QK-norm) of the group's q heads and of the new k; every item does it, only the owner of `pos` stores k/v
     const float *cs = at.cos_t + (size_t)pos * HALF, *sn = at.sin_t + (size_t)pos * HALF;
-    for (int idx = tid; idx < (group + 1) * HALF; idx += MG_CONSUMERS) {
+    for (int idx = tid; idx < (group + 1) * HALF; idx += NT) {
         const int hh = idx / HALF, i = idx % HALF;
         const bool isk = hh == group;
         const float *src = isk ? at.k + kvh * HD : at.q + (size_t)(kvh * group + hh) * HD;
@@ -405,7 +407,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
     }
     if (tid < HD) S.v[tid] = at.v[kvh * HD + tid];
     if (tid < group) { S.m_run[tid] = -INFINITY; S.l_run[tid] = 0.f; S.corr[tid] = 0.f; }
-    mega_consumer_bar();
+    cons_bar<NT>();
     if (at.qk_norm) {
         if (warp <= group) {  // RMSNormBare, go/quant.go:584-594
             float *vec = warp == group ? S.k : S.q[warp];
@@ -415,7 +417,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
             const float inv = (float)(1.0 / sqrt(ss / (double)HD + (double)at.eps));
             for (int i = lane; i < HD; i += 32) vec[i] *= inv;
         }
-        mega_consumer_bar();
+        cons_bar<NT>();
     }
     // exactly one item per kv head has a range that ends at n and is not empty: it owns position `pos` and stores the new row
     if (t_begin < n && t_end == n && tid < HD) {
@@ -425,7 +427,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
 
     // PV work split: thread = (position-interleaved part, head in group, dim)
     const int threads_per_part = group * HD;
-    int nparts = MG_CONSUMERS / threads_per_part;
+    int nparts = NT / threads_per_part;
     if (nparts > 3) nparts = 3;
     const int my_part = tid / threads_per_part, my_h = (tid % threads_per_part) / HD, my_d = tid % HD;
     float acc = 0.f;
@@ -433,7 +435,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
     const int sub = tid & 7, tg = tid >> 3;  // scores: 8 lanes per position, 96 positions per pass
     for (int c0 = t_begin; c0 < t_end; c0 += MG_ATT_CHUNK) {
         const int cn = min(c0 + MG_ATT_CHUNK, t_end) - c0;
-        for (int tb = 0; tb < cn; tb += MG_CONSUMERS / 8) {
+        for (int tb = 0; tb < cn; tb += NT / 8) {
             const int tl = tb + tg, t = c0 + tl;
             const bool valid = tl < cn;
             float kreg[8];
@@ -455,7 +457,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
                 if (sub == 0 && valid) S.sc[hh][tl] = dot * at.scale;
             }
         }
-        mega_consumer_bar();
+        cons_bar<NT>();
         if (warp < group) {  // running softmax statistics of head `warp` (flash-decoding form of go/quant.go:610-626)
             float mx = -INFINITY;
             for (int i = lane; i < cn; i += 32) mx = fmaxf(mx, S.sc[warp][i]);
@@ -472,7 +474,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
                 S.m_run[warp] = m_new;
             }
         }
-        mega_consumer_bar();
+        cons_bar<NT>();
         if (my_part < nparts) {
             float a = acc * S.corr[my_h];
             for (int tl = my_part; tl < cn; tl += nparts) {
@@ -482,10 +484,10 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
             }
             acc = a;
         }
-        mega_consumer_bar();
+        cons_bar<NT>();
     }
     if (my_part < nparts) S.pv[my_part][my_h][my_d] = acc;
-    mega_consumer_bar();
+    cons_bar<NT>();
     if (tid < threads_per_part) {
         float o = 0.f;
         for (int p = 0; p < nparts; p++) o += S.pv[p][my_h][my_d];
@@ -499,13 +501,13 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
     // The split that arrives last on this kv head folds all splits (fixed order => deterministic) and publishes the final
     // attention output, so the O-projection reads one plain vector instead of every CTA re-reading all partials.
     __threadfence();
-    mega_consumer_bar();
+    cons_bar<NT>();
     if (tid == 0) {
         unsigned int old;
         asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(at.split_cnt + layer * at.n_kv_heads + kvh) : "memory");
         S.is_last = (old == (unsigned)at.nsplit - 1u);
     }
-    mega_consumer_bar();
+    cons_bar<NT>();
     if (S.is_last && tid < threads_per_part) {
         const int h = kvh * group + my_h;
         float M = -INFINITY;
@@ -522,7 +524,7 @@ __device__ __forceinline__ void attn_item(const MegaAttn &at, int layer, int ite
         o *= 1.0f / den;
         for (int r = 0; r < at.out_reps; r++) at.out[(size_t)r * at.out_stride + h * HD + my_d] = o;
     }
-    mega_consumer_bar();  // S is reused by the next item of this CTA
+    cons_bar<NT>();  // S is reused by the next item of this CTA
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -663,7 +665,7 @@ __global__ void __launch_bounds__(MG_THREADS, 1) decode_mega_kernel(const MegaAr
         if (P.kind == PH_ATTN) {
             if (tid == 0) { *(volatile int *)&hold_flag = p; *(volatile int *)&hold1_flag = 0; }
             const int n_items = A.at.n_kv_heads * A.at.nsplit;
-            for (int item = blockIdx.x; item < n_items; item += G) attn_item(A.at, P.layer, item, att, tid);
+            for (int item = blockIdx.x; item < n_items; item += G) attn_item<MG_CONSUMERS>(A.at, P.layer, item, att, tid);
             __threadfence();
             mega_consumer_bar();
             if (tid == 0) { MG_TRACE(p, 3); phase_arrive(A.bar, p); MG_TRACE(p, 4); }

@@ -1,0 +1,80 @@
+// nl_tile.cuh — batch-1 decode on tensor cores: persistent per-token kernel over MMA-fragment-tiled Q4_0 weights (sm_100a).
+//
+// Replaces (*LlamaModel).Forward, go/model.go:490-620, with MatMulQ4_0 (go/quant.go:45-94) as the hot loop.
+//
+// Why tensor cores for a GEMV: at HBM speed each SM sub-partition must retire ~12 Q4_0 weights per cycle; turning
+// every nibble into an fp32 operand on the ALU pipe (one PRMT each) caps a CUDA-core kernel near half the HBM roofline
+// (profiles/r01_gemv_stream_full.md).  Here a nibble becomes an MMA operand with 0.625 ALU ops: masked in place it IS an
+// fp16 subnormal (n * 2^-24, or 16n * 2^-24 one nibble higher), so `mma.sync.m16n8k16` (A = 16 weight rows x 16 nibbles,
+// straight from the packed words; B = the activation vector) does the multiply-adds.  Products are exact, accumulation is
+// fp32.  The activation x (fp32) enters as an exact-to-2^-22 pair of fp16 terms (hi + lo) in two B columns; four quant
+// blocks share one accumulator fragment by giving each block its own column pair, so the per-block scale d (applied AFTER
+// the block dot like the reference, quant.go:88) costs one FMA per (row, block) on a fully used warp.
+//
+// Weight layout ("tiles"): 16 rows x 4 blocks (128 columns) = 1152 contiguous bytes, already in fragment order:
+//     [   0, 512)  lane (g,t) -> 16 B: nibbles of block (row g,   blk t)      g = lane >> 2, t = lane & 3
+//     [ 512,1024)  lane (g,t) -> 16 B: nibbles of block (row g+8, blk t)
+//     [1024,1152)  lane (g,t) ->  4 B: fp16 d(row g, blk t), fp16 d(row g+8, blk t)
+// Same bytes as the GGUF tensor (18 B per block), tiles of a 16-row group contiguous, row groups consecutive: a CTA's share
+// of a matrix is ONE byte range, moved through a shared-memory ring with cp.async.bulk; every LDS is a conflict-free 512-B
+// warp access.
+//
+// Kernel structure (one CTA per SM, cooperative): 16 math warps + 1 copy warp + 1 finishing warp walk the phase list
+//     per layer: QKV (RMSNorm fused) | attention | O (+residual) | gate/up (RMSNorm fused, SiLU*up) | down (+residual);  LM head
+// separated by grid barriers (one counter per phase).  The copy warp never waits for a barrier (weights do not depend on
+// activations), so the ring keeps HBM busy across phase boundaries.  Per ring slot (32 tiles) each math warp owns two tiles and
+// drops per-row partial sums into shared memory; the finishing warp adds them in a fixed order (deterministic), keeps the
+// running sum of a row group across slots, applies bias / residual / SiLU*up and publishes the outputs.
+#pragma once
+#include "nl_common.cuh"
+#include "nl_stream.cuh"  // PTX wrappers
+#include "nl_mega.cuh"    // MegaAttn, attn_item, grid-barrier helpers
+
+namespace nl {
+
+constexpr int TL_CW = 16;                          // math warps
+constexpr int TL_CONSUMERS = TL_CW * 32;           // 512
+constexpr int TL_THREADS = TL_CONSUMERS + 64;      // + copy warp + finishing warp
+constexpr int TL_TILE = 1152;                      // bytes per tile (16 rows x 4 blocks of Q4_0)
+constexpr int TL_TS = 2 * TL_CW;                   // tiles per ring slot: two per math warp
+constexpr int TL_SLOT_BYTES = TL_TS * TL_TILE;     // 36,864
+constexpr int TL_SLOTS = 4;
+constexpr int TL_MAX_NBG = 96;                     // block groups per row: cols <= 12,288
+constexpr int TL_XFRAG_BYTES = TL_MAX_NBG * 512;   // fp16 hi/lo fragments of the phase input
+constexpr int TL_MAX_ITEMS = 3;                    // 8-float items per math thread in the prologue
+constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_MAX_NBG * 4 * 4;
+
+enum { TEPI_STORE = 0, TEPI_RESID = 1, TEPI_SWIGLU = 2 };
+
+struct TilePhase {
+    int kind;                 // PH_GEMV / PH_ATTN
+    int layer;                // PH_ATTN
+    const uint8_t *tiles;     // tiled matrix: n_rg row groups x nbg tiles
+    int n_rg, nbg;
+    unsigned int nbg_magic;   // ceil(2^32 / nbg): tile index -> row group without a divide
+    int unit_rg;              // row groups per distribution unit (2 for gate/up: gate group, then the up group of the same rows)
+    int cols;                 // input length (multiple of 32)
+    int rows;                 // valid output rows (<= 16 * n_rg / unit_rg for SWIGLU, <= 16 * n_rg otherwise)
+    int epi;                  // TEPI_*
+    const float *x;           // input vector [cols]
+    const float *norm_w;      // non-null: input is RMSNorm(x; norm_w), go/quant.go:597-607
+    const float *bias;        // optional [rows]
+    float *out;               // output vector
+};
+
+struct TileArgs {
+    const TilePhase *phases;
+    int n_phases;
+    unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
+    MegaAttn at;
+    float eps;
+    unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
+};
+
+// planar (qs, d) -> tiles: row group R of the source lands at tile row group rg_off + R * rg_stride (gate/up interleave: stride 2,
+// offsets 0 / 1; q,k,v concatenation: stride 1, running offsets).  Rows / blocks beyond the matrix become zero blocks (d = 0).
+int launch_tile_q4_0(const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st);
+int launch_tiled(const TileArgs &a, int grid, cudaStream_t st);
+inline unsigned int tile_magic(int nbg) { return nbg <= 1 ? 0u : (unsigned int)(((1ull << 32) + (unsigned)nbg - 1) / (unsigned)nbg); }
+
+}  // namespace nl

