@@ -270,7 +270,9 @@ struct nl_model {
     // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
     bool tile_ok = false;
     std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
-    float *qkv = nullptr;               // [qdim + 2 kvd] contiguous q | k | v of the tiled path
+    // flagged {value, flag} activation vectors of the tiled path: residual stream, q | k | v, attention output, SwiGLU output
+    uint2 *x_ll = nullptr, *qkv_ll = nullptr, *ao_ll = nullptr, *hb_ll = nullptr;
+    unsigned int *d_epoch = nullptr;    // launch counter behind the flags
     float *qkv_bias = nullptr;
     TilePhase *d_tphases = nullptr; TileArgs targs; int tile_grid = 0;
     int act_stride = 0;          // floats between the MG_REPS copies of x / xb2 / hb (replica 0 is what every other path uses)
@@ -419,12 +421,15 @@ static int make_tiles(uint8_t **dst, const DevMat *const *mats, int n, bool inte
     }
     return NL_OK;
 }
-static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const float *x, const float *norm_w,
-                            const float *bias, float *out) {
+// in / out / resid are plain fp32 vectors, or flagged pair vectors when the matching *_ll is set
+static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const void *x, int in_ll,
+                            const float *norm_w, const float *bias, void *out, int out_ll, const void *resid = nullptr, int resid_ll = 0) {
     memset(&P, 0, sizeof P);
     P.kind = PH_GEMV; P.tiles = tiles; P.n_rg = n_rg; P.nbg = (cols / 32 + 3) / 4; P.nbg_magic = tile_magic(P.nbg); P.unit_rg = unit_rg;
-    P.cols = cols; P.rows = rows; P.epi = epi; P.x = x; P.norm_w = norm_w; P.bias = bias; P.out = out;
+    P.cols = cols; P.rows = rows; P.epi = epi; P.x = (const float *)x; P.norm_w = norm_w; P.bias = bias; P.out = (float *)out;
+    P.resid = (const float *)resid; P.in_ll = in_ll; P.out_ll = out_ll; P.resid_ll = resid_ll;
 }
+__global__ void bump_epoch_kernel(unsigned int *epoch) { *epoch += 1; }
 
 // Phase list of the tiled persistent kernel.  Leaves tile_ok = false when the model does not fit (types other than Q4_0, rows not a
 // multiple of 16, head_dim != 64, tensor parallel ...): the per-matrix kernels are used then.
@@ -443,8 +448,12 @@ static int build_tiled(nl_model *m) {
     const int G = m->opts.num_sms;
     const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size, nqkv = qdim + 2 * kvd;
     cudaStream_t st = m->st;
-    NL_CUDA(cudaMalloc(&m->qkv, (size_t)nqkv * 4));
-    NL_CUDA(cudaMemset(m->qkv, 0, (size_t)nqkv * 4));
+    {
+        struct { uint2 **p; int n; } ll[4] = {{&m->x_ll, dim}, {&m->qkv_ll, nqkv}, {&m->ao_ll, qdim}, {&m->hb_ll, ffn}};
+        for (auto &b : ll) { NL_CUDA(cudaMalloc(b.p, (size_t)b.n * 8)); NL_CUDA(cudaMemset(*b.p, 0, (size_t)b.n * 8)); }
+        NL_CUDA(cudaMalloc(&m->d_epoch, 4));
+        NL_CUDA(cudaMemset(m->d_epoch, 0, 4));
+    }
     if (any_bias) {   // q | k | v biases in the same order as the concatenated rows (absent ones are zero)
         NL_CUDA(cudaMalloc(&m->qkv_bias, (size_t)c.n_layers * nqkv * 4));
         NL_CUDA(cudaMemset(m->qkv_bias, 0, (size_t)c.n_layers * nqkv * 4));
@@ -471,14 +480,16 @@ static int build_tiled(nl_model *m) {
         m->tile_bufs.push_back(t_gu);
         if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_dn);
-        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, m->x, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv);
+        // layer 0 reads the embedding kernel's plain x; from then on the residual stream lives in x_ll
+        const void *x_in = l == 0 ? (const void *)m->x : (const void *)m->x_ll;
+        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv_ll, 1);
         ph.push_back(P);
         memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
-        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->xb2, nullptr, ly.bo, m->x);
+        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, 1, nullptr, ly.bo, m->x_ll, 1, x_in, l > 0);
         ph.push_back(P);
-        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, m->x, ly.ffn_norm, nullptr, m->hb);
+        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, m->x_ll, 1, ly.ffn_norm, nullptr, m->hb_ll, 1);
         ph.push_back(P);
-        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb, nullptr, nullptr, m->x);
+        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, 1, nullptr, nullptr, m->x_ll, 1, m->x_ll, 1);
         ph.push_back(P);
     }
     {
@@ -486,7 +497,7 @@ static int build_tiled(nl_model *m) {
         const DevMat *lm[1] = {&outw};
         if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_lm);
-        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, m->x, m->output_norm, nullptr, m->logits);
+        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, m->x_ll, 1, m->output_norm, nullptr, m->logits, 0);
         ph.push_back(P);
     }
     NL_CUDA(cudaStreamSynchronize(st));
@@ -501,11 +512,12 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps;
-    a.at.q = m->qkv; a.at.k = m->qkv + qdim; a.at.v = m->qkv + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch;
+    // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
+    a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
     a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
-    a.at.nsplit = nsplit; a.at.out = m->xb2; a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
+    a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_ll); a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
     a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
         NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
@@ -532,6 +544,8 @@ static int record_forward(nl_model *m, int batch) {
     if (batch == 1 && m->tile_ok) {
         // everything after the embedding in ONE persistent tensor-core kernel (nl_tile.cuh); its grid-barrier counters start at zero
         NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
+        bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
+        launches++;
         if (launch_tiled(m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         launches++;
         NL_CUDA(cudaGetLastError());
@@ -916,7 +930,7 @@ void nl_destroy(nl_model *m) {
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
-    if (m->qkv) cudaFree(m->qkv);
+    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
     if (m->d_tphases) cudaFree(m->d_tphases);
     if (m->d_phases) cudaFree(m->d_phases);
@@ -1194,7 +1208,7 @@ static int matrix_tiles(nl_matrix *w, int n_copies) {
         if (!w->d_tbar) { NL_CUDA(cudaMalloc(&w->d_tbar, 4)); NL_CUDA(cudaMemset(w->d_tbar, 0, 4)); }
         std::vector<TilePhase> ph(n_copies);
         for (int i = 0; i < n_copies; i++)
-            tile_gemv_phase(ph[i], w->tiles[i], (int)(m0.rows / 16), (int)m0.cols, 1, (int)m0.rows, TEPI_STORE, w->x, nullptr, nullptr, w->out);
+            tile_gemv_phase(ph[i], w->tiles[i], (int)(m0.rows / 16), (int)m0.cols, 1, (int)m0.rows, TEPI_STORE, w->x, 0, nullptr, nullptr, w->out, 0);
         NL_CUDA(cudaMalloc(&w->d_tph, n_copies * sizeof(TilePhase)));
         NL_CUDA(cudaMemcpy(w->d_tph, ph.data(), n_copies * sizeof(TilePhase), cudaMemcpyHostToDevice));
         w->tph_cap = n_copies;
@@ -1203,7 +1217,7 @@ static int matrix_tiles(nl_matrix *w, int n_copies) {
 }
 static int matrix_tiled_gemv(nl_matrix *w, int idx) {
     TileArgs a; memset(&a, 0, sizeof a);
-    a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar;
+    a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar; a.inflight = tile_inflight();
     const int units = (int)(w->copies[0].rows / 16);
     if (launch_tiled(a, units < w->opts.num_sms ? units : w->opts.num_sms, w->st)) return fail(NL_ERR_CUDA, "tiled gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return NL_OK;

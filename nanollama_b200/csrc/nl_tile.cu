@@ -48,17 +48,72 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
 }
 #define TL_TRACE(p, k) do { if (A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
 
-// One tile: 16 rows x 4 blocks.  acc0 / acc1: this lane's running sums for (row g, block column t) and (row g+8, t).
-__device__ __forceinline__ void tile_dot(const uint8_t *tp, const uint8_t *xfrag_b, const float corr_v, bool xact, int lane, uint32_t (&xb)[16],
-                                         float &acc0, float &acc1) {
-    const uint4 wa4 = *reinterpret_cast<const uint4 *>(tp + lane * 16);
-    const uint4 wb4 = *reinterpret_cast<const uint4 *>(tp + 512 + lane * 16);
-    const uint32_t dd = *reinterpret_cast<const uint32_t *>(tp + 1024 + lane * 4);
-    if (xact) {   // only the lane that owns (block column, hi|lo) of B holds data; every other lane keeps zeros
-        const uint4 *xp = reinterpret_cast<const uint4 *>(xfrag_b);
+// ---- flagged activations ("LL" format): every fp32 element travels as an 8-byte {value, flag} pair written by ONE store, so a reader
+// that sees the expected flag has the value too and no fence is needed between a phase's output stores and its arrival on the grid
+// barrier (the barrier only tells the readers when looking is worthwhile).  flag = epoch * (n_phases + 1) + producing phase + 1.
+__device__ __forceinline__ void st_ll(void *base, int idx, float v, unsigned int flag) {
+    asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2 *>(base) + idx), "r"(__float_as_uint(v)), "r"(flag) : "memory");
+}
+__device__ __forceinline__ float ld_ll_value(const void *base, int idx) {   // value of an element known to be complete
+    return __uint_as_float(__ldcg(reinterpret_cast<const unsigned int *>(base) + 2 * idx));
+}
+__device__ __forceinline__ float ld_ll_wait(const void *base, int idx, unsigned int want) {
+    unsigned int v, f;
+    do {
+        asm volatile("ld.volatile.global.v2.u32 {%0, %1}, [%2];" : "=r"(v), "=r"(f) : "l"(reinterpret_cast<const uint2 *>(base) + idx) : "memory");
+    } while (f != want);
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+// fence-free grid barrier: relaxed arrive, relaxed poll (correctness comes from the flags in the data)
+__device__ __forceinline__ void arrive_relaxed(unsigned int *bar, int p) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar + p) : "memory"); }
+__device__ __forceinline__ void wait_relaxed(const unsigned int *bar, int p, unsigned int G) {
+    unsigned int v;
+    do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + p) : "memory");
+    } while (v < G);
+}
+
+// shared-memory accessors on raw 32-bit shared addresses (all address arithmetic stays in 32-bit integer registers, computed once)
+__device__ __forceinline__ uint4 lds128(uint32_t a) {
+    uint4 v;
+    asm volatile("ld.shared.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ uint32_t lds32(uint32_t a) {
+    uint32_t v;
+    asm volatile("ld.shared.u32 %0, [%1];" : "=r"(v) : "r"(a));
+    return v;
+}
+__device__ __forceinline__ void sts32f(uint32_t a, float v) { asm volatile("st.shared.f32 [%0], %1;" ::"r"(a), "f"(v) : "memory"); }
+__device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_u(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
+
+// B fragments of one block group: only the lane that owns (block column, hi|lo) of B holds data, every other lane keeps zeros
+__device__ __forceinline__ void load_xb(uint32_t xf_lane, int B, bool xact, uint32_t (&xb)[16]) {
+    if (xact) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const uint4 v = xp[i]; xb[4 * i] = v.x; xb[4 * i + 1] = v.y; xb[4 * i + 2] = v.z; xb[4 * i + 3] = v.w; }
+        for (int i = 0; i < 4; i++) { const uint4 v = lds128(xf_lane + (uint32_t)B * 512u + 16u * i); xb[4 * i] = v.x; xb[4 * i + 1] = v.y; xb[4 * i + 2] = v.z; xb[4 * i + 3] = v.w; }
     }
+}
+// One tile: 16 rows x 4 blocks.  acc0 / acc1: this lane's running sums for (row g, block column t) and (row g+8, t).
+// tile_lane = shared address of the tile + 16 * lane.
+__device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, const float corr_v, const uint32_t (&xb)[16], float &acc0, float &acc1) {
+    const uint4 wa4 = lds128(tile_lane);
+    const uint4 wb4 = lds128(tile_lane + 512u);
+    const uint32_t dd = lds32(d_lane);
     const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
     float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -76,6 +131,233 @@ __device__ __forceinline__ void tile_dot(const uint8_t *tp, const uint8_t *xfrag
     acc1 = fmaf(df.y, v1, acc1);
 }
 
+// ---------------------------------------------------------------------------------------------------------------------
+// Attention phase (go/model.go:530-587): item = (kv head, split of the positions).  The K/V rows of earlier positions do not depend on
+// the current token, so an item's first 64 rows are fetched into shared memory (cp.async) BEFORE the grid barrier that publishes
+// q / k / v; after the barrier one round trip brings q, k, v, everything else is on chip.  Short contexts use one split per
+// 64 positions (a single split writes the final output directly, no cross-CTA combine); longer ones use up to at.nsplit splits
+// whose un-normalised partials (flash-decoding) are folded by the split that arrives last (fixed order => deterministic).
+constexpr int TA_CH = 64;   // positions per pass
+struct AttnT {              // lives in the fragment buffer during the attention phase
+    float q[MG_MAX_GROUP][64];
+    float knew[64], vnew[64];
+    float p[MG_MAX_GROUP][TA_CH];
+    float Ks[TA_CH][68];    // 272-byte rows: 16-byte aligned, and 8 consecutive rows hit 8 different bank groups
+    float Vs[TA_CH][64];
+    float pv[TL_CONSUMERS];
+    float m_run[MG_MAX_GROUP], l_run[MG_MAX_GROUP], corr[MG_MAX_GROUP];
+    int is_last;
+};
+static_assert(sizeof(AttnT) <= TL_XFRAG_BYTES, "attention scratch must fit the fragment buffer");
+
+__device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
+}
+__device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
+
+struct AttnItem { int kvh, sp, nse, t_begin, t_end; };
+__device__ __forceinline__ AttnItem attn_locate(const MegaAttn &at, int item, int n, int nse) {
+    AttnItem I;
+    I.kvh = item / nse; I.sp = item - I.kvh * nse; I.nse = nse;
+    const int per = (n + nse - 1) / nse;
+    I.t_begin = min(I.sp * per, n); I.t_end = min(I.t_begin + per, n);
+    return I;
+}
+// rows [t0, t0 + cn) below `pos` of the K and V cache of one kv head -> S.Ks / S.Vs (asynchronous)
+__device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int kvd, int kvh, int t0, int cn, int pos, AttnT &S, int tid) {
+    for (int idx = tid; idx < cn * 32; idx += TL_CONSUMERS) {
+        const int tl = idx >> 5, f = idx & 31, t = t0 + tl;
+        if (t < pos) {
+            if (f < 16) cp_async16(&S.Ks[tl][4 * f], kc + (size_t)t * kvd + kvh * 64 + 4 * f);
+            else cp_async16(&S.Vs[tl][4 * (f - 16)], vc + (size_t)t * kvd + kvh * 64 + 4 * (f - 16));
+        }
+    }
+}
+
+__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, AttnT &S, int tid,
+                                                unsigned int want, unsigned int oflag) {
+    constexpr int HD = 64, HALF = 32;
+    const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
+    const int warp = tid >> 5, lane = tid & 31;
+    const int kvh = I.kvh, n = pos + 1;
+    float *kc = at.kcache + (size_t)layer * at.seq_len * kvd, *vc = at.vcache + (size_t)layer * at.seq_len * kvd;
+    const bool owner = pos >= I.t_begin && pos < I.t_end;   // exactly one split per kv head holds the new position
+
+    // ---- RoPE of the group's q heads and of the new k (go/model.go:449-477, :530-539); v as it is
+    if (tid < (group + 1) * HALF) {
+        const int hh = tid >> 5, i = tid & 31;
+        const bool isk = hh == group;
+        // q | k | v are one flagged vector [H*hd + 2*kvd] (at.q = base; at.k / at.v are element offsets from it)
+        const int e0 = isk ? (int)(at.k - at.q) + kvh * HD : (kvh * group + hh) * HD;
+        const float x0 = ld_ll_wait(at.q, e0 + i, want), x1 = ld_ll_wait(at.q, e0 + i + HALF, want);
+        const float c = __ldg(at.cos_t + (size_t)pos * HALF + i), sn = __ldg(at.sin_t + (size_t)pos * HALF + i);
+        float r0, r1;
+        if (!at.conj) { r0 = x0 * c - x1 * sn; r1 = x0 * sn + x1 * c; }
+        else { r0 = x0 * c + x1 * sn; r1 = -x0 * sn + x1 * c; }
+        float *dst = isk ? S.knew : S.q[hh];
+        dst[i] = r0; dst[i + HALF] = r1;
+    } else if (tid >= TL_CONSUMERS - HD) {
+        S.vnew[tid - (TL_CONSUMERS - HD)] = ld_ll_wait(at.q, (int)(at.v - at.q) + kvh * HD + tid - (TL_CONSUMERS - HD), want);
+    }
+    if (tid < group) { S.m_run[tid] = -INFINITY; S.l_run[tid] = 0.f; S.corr[tid] = 0.f; }
+    tl_bar<TL_CONSUMERS>();
+    if (at.qk_norm) {
+        if (warp <= group) {  // RMSNormBare, go/quant.go:584-594
+            float *vec = warp == group ? S.knew : S.q[warp];
+            double ss = 0.0;
+            for (int i = lane; i < HD; i += 32) ss += (double)vec[i] * (double)vec[i];
+            ss = warp_sum_d(ss);
+            const float inv = (float)(1.0 / sqrt(ss / (double)HD + (double)at.eps));
+            for (int i = lane; i < HD; i += 32) vec[i] *= inv;
+        }
+        tl_bar<TL_CONSUMERS>();
+    }
+    if (owner && tid < HD) {   // KV write, go/model.go:552-554
+        kc[(size_t)pos * kvd + kvh * HD + tid] = S.knew[tid];
+        vc[(size_t)pos * kvd + kvh * HD + tid] = S.vnew[tid];
+    }
+
+    const int gthreads = group * HD;                       // one thread per (head of the group, dim | position)
+    const int nparts = TL_CONSUMERS / gthreads;            // PV: positions interleaved over nparts thread sets
+    const int part = tid / gthreads, rem = tid - part * gthreads, hh = rem >> 6, dd = rem & 63;
+    float acc = 0.f;
+    for (int c0 = I.t_begin; c0 < I.t_end; c0 += TA_CH) {
+        const int cn = min(TA_CH, I.t_end - c0);
+        if (!(prefetched && c0 == I.t_begin)) attn_fetch(kc, vc, kvd, kvh, c0, cn, pos, S, tid);
+        if (owner && pos >= c0 && pos < c0 + cn) {          // the new position's row comes from this token's k / v
+            if (tid < HD) S.Ks[pos - c0][tid] = S.knew[tid];
+            else if (tid < 2 * HD) S.Vs[pos - c0][tid - HD] = S.vnew[tid - HD];
+        }
+        cp_async_wait_all();
+        tl_bar<TL_CONSUMERS>();
+        if (tid < gthreads && dd < cn) {                    // scores: thread = (head hh, position dd)
+            const float4 *kp = reinterpret_cast<const float4 *>(&S.Ks[dd][0]), *qp = reinterpret_cast<const float4 *>(&S.q[hh][0]);
+            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
+#pragma unroll
+            for (int j = 0; j < 16; j++) {
+                const float4 kk = kp[j], qq = qp[j];
+                d0 = fmaf(qq.x, kk.x, d0); d1 = fmaf(qq.y, kk.y, d1); d2 = fmaf(qq.z, kk.z, d2); d3 = fmaf(qq.w, kk.w, d3);
+            }
+            S.p[hh][dd] = ((d0 + d1) + (d2 + d3)) * at.scale;
+        }
+        tl_bar<TL_CONSUMERS>();
+        if (warp < group) {  // running softmax statistics of head `warp` (flash-decoding form of go/quant.go:610-626)
+            const float s0 = lane < cn ? S.p[warp][lane] : -INFINITY, s1 = lane + 32 < cn ? S.p[warp][lane + 32] : -INFINITY;
+            const float mx = warp_max(fmaxf(s0, s1));
+            const float m_old = S.m_run[warp], m_new = fmaxf(m_old, mx);
+            const float e0 = lane < cn ? expf(s0 - m_new) : 0.f, e1 = lane + 32 < cn ? expf(s1 - m_new) : 0.f;
+            if (lane < cn) S.p[warp][lane] = e0;
+            if (lane + 32 < cn) S.p[warp][lane + 32] = e1;
+            const float sum = warp_sum(e0 + e1);
+            if (lane == 0) {
+                const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
+                S.corr[warp] = corr;
+                S.l_run[warp] = S.l_run[warp] * corr + sum;
+                S.m_run[warp] = m_new;
+            }
+        }
+        tl_bar<TL_CONSUMERS>();
+        if (part < nparts) {
+            float a = acc * S.corr[hh];
+            for (int tl = part; tl < cn; tl += nparts) a = fmaf(S.p[hh][tl], S.Vs[tl][dd], a);
+            acc = a;
+        }
+        tl_bar<TL_CONSUMERS>();
+    }
+    S.pv[tid] = acc;
+    tl_bar<TL_CONSUMERS>();
+    if (tid < gthreads) {
+        float o = 0.f;
+        for (int pp = 0; pp < nparts; pp++) o += S.pv[pp * gthreads + tid];
+        const int h = kvh * group + hh;
+        if (I.nse == 1) {
+            st_ll(at.out, h * HD + dd, o * (1.0f / S.l_run[hh]), oflag);
+        } else {
+            at.part_acc[((size_t)(h * at.nsplit + I.sp)) * HD + dd] = o;
+            if (dd == 0) {
+                at.part_ml[(h * at.nsplit + I.sp) * 2] = S.m_run[hh];
+                at.part_ml[(h * at.nsplit + I.sp) * 2 + 1] = S.l_run[hh];
+            }
+        }
+    }
+    if (I.nse > 1) {
+        __threadfence();
+        tl_bar<TL_CONSUMERS>();
+        if (tid == 0) {
+            unsigned int old;
+            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(at.split_cnt + layer * at.n_kv_heads + kvh) : "memory");
+            S.is_last = (old == (unsigned)I.nse - 1u);
+        }
+        tl_bar<TL_CONSUMERS>();
+        if (S.is_last && tid < gthreads) {
+            const int h = kvh * group + hh;
+            float M = -INFINITY;
+            for (int s = 0; s < I.nse; s++) M = fmaxf(M, __ldcg(at.part_ml + (h * at.nsplit + s) * 2));
+            float den = 0.f, o = 0.f;
+            for (int s = 0; s < I.nse; s++) {
+                const float m = __ldcg(at.part_ml + (h * at.nsplit + s) * 2), l = __ldcg(at.part_ml + (h * at.nsplit + s) * 2 + 1);
+                if (l > 0.f) {
+                    const float wgt = expf(m - M);
+                    den = fmaf(wgt, l, den);
+                    o = fmaf(wgt, __ldcg(at.part_acc + ((size_t)(h * at.nsplit + s)) * HD + dd), o);
+                }
+            }
+            st_ll(at.out, h * HD + dd, o * (1.0f / den), oflag);
+        }
+    }
+    tl_bar<TL_CONSUMERS>();  // S is reused by the next item of this CTA
+}
+
+// Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Kept out of line so that its registers (two sets of B
+// fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
+// My two tiles of slot k are band tiles 32k + 2 warp (+1); their block group advances by 32 mod nbg per slot.
+__device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, int warp, int lane, uint32_t ring_u, uint32_t xfrag_u,
+                                        uint32_t corr_u, uint32_t full_u, uint32_t empty_u, uint32_t red_lane) {
+    const int g = lane >> 2, t = lane & 3;
+    const bool xact = (t == (g >> 1));     // lane that holds B column g (block column g>>1, hi|lo = g&1)
+    uint32_t xb0[16], xb1[16];             // B fragments of my two tiles (reloaded only when the block group changes)
+#pragma unroll
+    for (int i = 0; i < 16; i++) { xb0[i] = 0u; xb1[i] = 0u; }
+    uint32_t tile_lane0 = ring_u + (uint32_t)(2 * warp) * TL_TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
+    uint32_t d_lane0 = ring_u + (uint32_t)(2 * warp) * TL_TILE + 1024u + (uint32_t)lane * 4u;
+    uint32_t xf_lane = xfrag_u + (uint32_t)g * 64u, corr_lane = corr_u + (uint32_t)t * 4u;
+    asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(corr_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
+    int B = 2 * warp - rg_of(2 * warp, nbg, magic) * nbg;
+    const int stepB = TL_TS - rg_of(TL_TS, nbg, magic) * nbg;
+    int cb0 = -1, cb1 = -1;                // block groups whose fragments xb0 / xb1 hold
+    for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
+        const uint32_t slot = (uint32_t)it % TL_SLOTS;
+        const int n = min(TL_TS, band - c0);
+        mbar_wait_u(full_u + slot * 8u, ((uint32_t)it / TL_SLOTS) & 1u);
+        if (2 * warp < n) {
+            const uint32_t so = slot * (uint32_t)TL_SLOT_BYTES, ro = red_lane + slot * (uint32_t)(TL_CW * 2 * 16 * 4);
+            float acc0 = 0.f, acc1 = 0.f;
+            if (B != cb0) { load_xb(xf_lane, B, xact, xb0); cb0 = B; }
+            tile_dot(tile_lane0 + so, d_lane0 + so, __uint_as_float(lds32(corr_lane + (uint32_t)B * 16u)), xb0, acc0, acc1);
+            uint32_t eo = 0;
+            if (2 * warp + 1 < n) {
+                int B1 = B + 1;
+                if (B1 == nbg) {   // my second tile starts the next row group: flush the first
+                    acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+                    acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+                    if (t == 0) { sts32f(ro, acc0); sts32f(ro + 32u, acc1); }
+                    acc0 = 0.f; acc1 = 0.f; B1 = 0; eo = 64u;
+                }
+                if (B1 != cb1) { load_xb(xf_lane, B1, xact, xb1); cb1 = B1; }
+                tile_dot(tile_lane0 + so + TL_TILE, d_lane0 + so + TL_TILE, __uint_as_float(lds32(corr_lane + (uint32_t)B1 * 16u)), xb1, acc0, acc1);
+            }
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
+            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            if (t == 0) { sts32f(ro + eo, acc0); sts32f(ro + eo + 32u, acc1); }
+        }
+        B += stepB;
+        if (B >= nbg) B -= nbg;
+        __syncwarp();
+        if (lane == 0) mbar_arrive_u(empty_u + slot * 8u);
+    }
+    return it;
+}
+
 struct TlShared {
     uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
     float red[TL_SLOTS][TL_CW][2][16];
@@ -91,11 +373,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     uint8_t *ring = smem;
     uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
     float *corr = reinterpret_cast<float *>(xfrag + TL_XFRAG_BYTES);
-    AttnSmem &att = *reinterpret_cast<AttnSmem *>(xfrag);   // the attention phase has no GEMV input: same bytes
-    static_assert(sizeof(AttnSmem) <= TL_XFRAG_BYTES, "attention scratch must fit the fragment buffer");
+    AttnT &att = *reinterpret_cast<AttnT *>(xfrag);   // the attention phase has no GEMV input: same bytes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
+    const unsigned int flag_base = (A.epoch ? __ldg(A.epoch) : 0u) * (unsigned)(A.n_phases + 1);
     if (tid == 0) {
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -119,6 +401,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
                 const int slot = it % TL_SLOTS;
                 if (it >= TL_SLOTS) mbar_wait(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
+                // at most `inflight` copies on the wire: bytes requested but not yet landed are queue in front of every other
+                // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
+                if (it >= A.inflight) mbar_wait(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
                 const uint32_t bytes = (uint32_t)min(TL_TS, band - c0) * TL_TILE;
                 mbar_expect_tx(&sh.full_bar[slot], bytes);
                 bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)c0 * TL_TILE, bytes, &sh.full_bar[slot], policy);
@@ -138,6 +423,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const unsigned int magic = __ldg(&P->nbg_magic);
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
+            const float *resid_src = ldg_ptr(&P->resid);
+            const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);
+            const unsigned int oflag = flag_base + (unsigned)p + 1u;
             int u0, u1;
             band_of(__ldg(&P->n_rg) / urg, blockIdx.x, G, u0, u1);
             const int band = (u1 - u0) * urg * nbg;
@@ -153,7 +441,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 int q_done = -1;
                 if (epi == TEPI_RESID && c0 > 0) {
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
-                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = __ldcg(out + r); }
+                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r); }
                 }
                 mbar_wait(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
                 if (c0 == 0) post = sh.post_scale[p & 1];
@@ -175,14 +463,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                             if ((rg & 1) == 0) gate = v;
                             else {
                                 const int r = (rg >> 1) * 16 + row;
-                                if (half == 0 && r < rows) out[r] = silu_f(gate) * v;          // SiLU(gate)*up, go/model.go:604-606
+                                if (half == 0 && r < rows) {                                   // SiLU(gate)*up, go/model.go:604-606
+                                    if (out_ll) st_ll(out, r, silu_f(gate) * v, oflag); else out[r] = silu_f(gate) * v;
+                                }
                             }
                         } else {
                             const int r = rg * 16 + row;
                             if (half == 0 && r < rows) {
                                 if (bias) v += __ldg(bias + r);
-                                if (epi == TEPI_RESID) v += (q == q_done) ? resid : __ldcg(out + r);   // X += W.x, go/model.go:592-594, :610-612
-                                out[r] = v;
+                                if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                if (out_ll) st_ll(out, r, v, oflag); else out[r] = v;
                             }
                         }
                     }
@@ -191,7 +481,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 if (lane == 0) mbar_arrive(&sh.free_bar[slot]);
             }
             __syncwarp();
-            if (lane == 0) { TL_TRACE(p, 4); phase_arrive(A.bar, p); }   // release: cumulative over the warp's stores
+            if (lane == 0) { TL_TRACE(p, 4); arrive_relaxed(A.bar, p); }   // no fence: the outputs carry their own flags
             __syncwarp();
         }
         return;
@@ -199,10 +489,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 
     // ===================== math warps =====================
     const int g = lane >> 2, t = lane & 3;
-    const bool xact = (t == (g >> 1));     // lane that holds B column g (block column g>>1, hi|lo = g&1)
-    uint32_t xb[16];
-#pragma unroll
-    for (int i = 0; i < 16; i++) xb[i] = 0u;
     int it = 0;
     if (warp == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.phases[0]);
@@ -222,17 +508,32 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         const int kind = P.kind, layer = P.layer, nbg = P.nbg, cols = P.cols;
         const unsigned int magic = P.nbg_magic;
         const float *px = P.x, *pnw = P.norm_w;
+        const int in_ll = P.in_ll;
         int u0, u1;
         band_of(P.n_rg / P.unit_rg, blockIdx.x, G, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
         if (kind == PH_ATTN) {
-            if (tid == 0) { TL_TRACE(p, 0); phase_wait(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
+            tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
+            const int pos = *A.at.pos, n = pos + 1;
+            int nse = (n + TA_CH - 1) / TA_CH;
+            nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
+            const int n_items = A.at.n_kv_heads * nse;
+            const int kvd = A.at.n_kv_heads * 64;
+            bool pre = false;
+            if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
+                const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse);
+                attn_fetch(A.at.kcache + (size_t)layer * A.at.seq_len * kvd, A.at.vcache + (size_t)layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
+                           min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
+                pre = true;
+            }
+            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
-            const int n_items = A.at.n_kv_heads * A.at.nsplit;
-            for (int item = blockIdx.x; item < n_items; item += G) attn_item<TL_CONSUMERS>(A.at, layer, item, att, tid);
-            __threadfence();
-            tl_bar<TL_CONSUMERS>();
-            if (tid == 0) { TL_TRACE(p, 3); phase_arrive(A.bar, p); TL_TRACE(p, 4); }
+            for (int item = blockIdx.x; item < n_items; item += G) {
+                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u);
+                pre = false;
+            }
+            tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores (they carry their own flags; the KV rows are for later tokens)
+            if (tid == 0) { TL_TRACE(p, 3); arrive_relaxed(A.bar, p); TL_TRACE(p, 4); }
             continue;
         }
 
@@ -251,7 +552,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             }
         }
         if (p > 0) {
-            if (tid == 0) { TL_TRACE(p, 0); phase_wait(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
@@ -262,8 +563,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         for (int r = 0; r < TL_MAX_ITEMS; r++) {
             const int q = tid + r * TL_CONSUMERS;
             if (q < nitem) {
-                const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
-                xv[r][0] = a.x; xv[r][1] = a.y; xv[r][2] = a.z; xv[r][3] = a.w; xv[r][4] = b.x; xv[r][5] = b.y; xv[r][6] = b.z; xv[r][7] = b.w;
+                if (in_ll) {   // 8 flagged elements = 64 bytes; look again until all eight carry this phase's input flag
+                    const uint4 *src = reinterpret_cast<const uint4 *>(px) + 4 * q;
+                    const unsigned int want = flag_base + (unsigned)p;
+                    uint4 a0, a1, a2, a3;
+                    do {
+                        a0 = ld_vol_v4(src); a1 = ld_vol_v4(src + 1); a2 = ld_vol_v4(src + 2); a3 = ld_vol_v4(src + 3);
+                    } while (a0.y != want || a0.w != want || a1.y != want || a1.w != want || a2.y != want || a2.w != want || a3.y != want || a3.w != want);
+                    xv[r][0] = __uint_as_float(a0.x); xv[r][1] = __uint_as_float(a0.z); xv[r][2] = __uint_as_float(a1.x); xv[r][3] = __uint_as_float(a1.z);
+                    xv[r][4] = __uint_as_float(a2.x); xv[r][5] = __uint_as_float(a2.z); xv[r][6] = __uint_as_float(a3.x); xv[r][7] = __uint_as_float(a3.z);
+                } else {
+                    const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
+                    xv[r][0] = a.x; xv[r][1] = a.y; xv[r][2] = a.z; xv[r][3] = a.w; xv[r][4] = b.x; xv[r][5] = b.y; xv[r][6] = b.z; xv[r][7] = b.w;
+                }
                 float s4 = 0.f;
 #pragma unroll
                 for (int i = 0; i < 8; i++) {
@@ -330,36 +642,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (tid == 0) TL_TRACE(p, 2);
 
         // ---- stream the band ----
-        for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
-            const int slot = it % TL_SLOTS;
-            const int n = min(TL_TS, band - c0);
-            mbar_wait(&sh.full_bar[slot], (it / TL_SLOTS) & 1);
-            const uint8_t *sb = ring + (size_t)slot * TL_SLOT_BYTES;
-            const int tl = 2 * warp;
-            if (tl < n) {
-                const int r0 = c0 + tl;
-                const int q0 = rg_of(r0, nbg, magic);
-                int B = r0 - q0 * nbg;
-                float acc0 = 0.f, acc1 = 0.f;
-                tile_dot(sb + (size_t)tl * TL_TILE, xfrag + (size_t)B * 512 + g * 64, corr[4 * B + t], xact, lane, xb, acc0, acc1);
-                int e = 0;
-                if (tl + 1 < n) {
-                    B++;
-                    if (B == nbg) {   // my second tile starts the next row group: flush the first
-                        acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-                        acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-                        if (t == 0) { sh.red[slot][warp][0][g] = acc0; sh.red[slot][warp][0][g + 8] = acc1; }
-                        acc0 = 0.f; acc1 = 0.f; B = 0; e = 1;
-                    }
-                    tile_dot(sb + (size_t)(tl + 1) * TL_TILE, xfrag + (size_t)B * 512 + g * 64, corr[4 * B + t], xact, lane, xb, acc0, acc1);
-                }
-                acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-                acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
-                if (t == 0) { sh.red[slot][warp][e][g] = acc0; sh.red[slot][warp][e][g + 8] = acc1; }
-            }
-            __syncwarp();
-            if (lane == 0) mbar_arrive(&sh.empty_bar[slot]);
-        }
+        it = stream_band(band, nbg, magic, it, warp, lane, smem_u32(ring), smem_u32(xfrag), smem_u32(corr), smem_u32(&sh.full_bar[0]),
+                         smem_u32(&sh.empty_bar[0]), smem_u32(&sh.red[0][warp][0][lane >> 2]));
         if (tid == 0) TL_TRACE(p, 3);
     }
 }

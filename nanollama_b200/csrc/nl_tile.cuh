@@ -26,6 +26,8 @@
 // drops per-row partial sums into shared memory; the finishing warp adds them in a fixed order (deterministic), keeps the
 // running sum of a row group across slots, applies bias / residual / SiLU*up and publishes the outputs.
 #pragma once
+#include <stdlib.h>
+
 #include "nl_common.cuh"
 #include "nl_stream.cuh"  // PTX wrappers
 #include "nl_mega.cuh"    // MegaAttn, attn_item, grid-barrier helpers
@@ -56,18 +58,22 @@ struct TilePhase {
     int cols;                 // input length (multiple of 32)
     int rows;                 // valid output rows (<= 16 * n_rg / unit_rg for SWIGLU, <= 16 * n_rg otherwise)
     int epi;                  // TEPI_*
-    const float *x;           // input vector [cols]
+    const float *x;           // input vector [cols]: plain fp32, or {value, flag} pairs when in_ll (see nl_tile.cu)
     const float *norm_w;      // non-null: input is RMSNorm(x; norm_w), go/quant.go:597-607
     const float *bias;        // optional [rows]
-    float *out;               // output vector
+    float *out;               // output vector (plain, or flagged pairs when out_ll)
+    const float *resid;       // TEPI_RESID: the vector the product is added to (plain, or flagged pairs when resid_ll)
+    int in_ll, out_ll, resid_ll;
 };
 
 struct TileArgs {
     const TilePhase *phases;
     int n_phases;
     unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
+    const unsigned int *epoch;  // launch counter behind the flags of the flagged activation vectors (null: no flagged vectors)
     MegaAttn at;
     float eps;
+    int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
 };
 
@@ -75,6 +81,11 @@ struct TileArgs {
 // offsets 0 / 1; q,k,v concatenation: stride 1, running offsets).  Rows / blocks beyond the matrix become zero blocks (d = 0).
 int launch_tile_q4_0(const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st);
 int launch_tiled(const TileArgs &a, int grid, cudaStream_t st);
+inline int tile_inflight() {
+    const char *e = getenv("NL_TILE_INFLIGHT");
+    int k = e ? atoi(e) : TL_SLOTS;
+    return k < 1 ? 1 : (k > TL_SLOTS ? TL_SLOTS : k);
+}
 inline unsigned int tile_magic(int nbg) { return nbg <= 1 ? 0u : (unsigned int)(((1ull << 32) + (unsigned)nbg - 1) / (unsigned)nbg); }
 
 }  // namespace nl
