@@ -468,6 +468,11 @@ static int build_tiled(nl_model *m) {
     std::vector<TilePhase> ph;
     TilePhase P;
     int rc;
+    // default: plain fp32 vectors (the pair buffers are then used as plain arrays) behind release / acquire barriers.
+    // NL_TILE_LL=1: flagged {value, flag} vectors with fence-free barriers -- measured slower on B200 (the arrival overtakes the
+    // data, the first look fails and costs a second L2 round trip; 2x the bytes per phase input), kept for experiments
+    const int LL = (getenv("NL_TILE_LL") && atoi(getenv("NL_TILE_LL")) == 1) ? 1 : 0;
+    void *xres = LL ? (void *)m->x_ll : (void *)m->x;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
         uint8_t *t_qkv = nullptr, *t_o = nullptr, *t_gu = nullptr, *t_dn = nullptr;
@@ -481,15 +486,15 @@ static int build_tiled(nl_model *m) {
         if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_dn);
         // layer 0 reads the embedding kernel's plain x; from then on the residual stream lives in x_ll
-        const void *x_in = l == 0 ? (const void *)m->x : (const void *)m->x_ll;
-        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv_ll, 1);
+        const void *x_in = (l == 0 || !LL) ? (const void *)m->x : (const void *)m->x_ll;
+        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, LL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv_ll, LL);
         ph.push_back(P);
         memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
-        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, 1, nullptr, ly.bo, m->x_ll, 1, x_in, l > 0);
+        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
         ph.push_back(P);
-        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, m->x_ll, 1, ly.ffn_norm, nullptr, m->hb_ll, 1);
+        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, LL, ly.ffn_norm, nullptr, m->hb_ll, LL);
         ph.push_back(P);
-        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, 1, nullptr, nullptr, m->x_ll, 1, m->x_ll, 1);
+        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, LL, nullptr, nullptr, xres, LL, xres, LL);
         ph.push_back(P);
     }
     {
@@ -497,7 +502,7 @@ static int build_tiled(nl_model *m) {
         const DevMat *lm[1] = {&outw};
         if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_lm);
-        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, m->x_ll, 1, m->output_norm, nullptr, m->logits, 0);
+        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, xres, LL, m->output_norm, nullptr, m->logits, 0);
         ph.push_back(P);
     }
     NL_CUDA(cudaStreamSynchronize(st));
@@ -508,11 +513,13 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMemcpy(m->d_tphases, ph.data(), ph.size() * sizeof(TilePhase), cudaMemcpyHostToDevice));
     const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
     NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
-    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 4));
-    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
+    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 8));   // flagged pairs
+    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 8));
+    NL_CUDA(cudaMemset(m->part_acc, 0, (size_t)c.n_heads * nsplit * 64 * 8));
+    NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)c.n_heads * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch;
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.ll = LL;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;

@@ -70,8 +70,13 @@ __device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
     return v;
 }
 // fence-free grid barrier: relaxed arrive, relaxed poll (correctness comes from the flags in the data)
-__device__ __forceinline__ void arrive_relaxed(unsigned int *bar, int p) { asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar + p) : "memory"); }
-__device__ __forceinline__ void wait_relaxed(const unsigned int *bar, int p, unsigned int G) {
+// (ll = false: plain vectors, release / acquire barrier)
+__device__ __forceinline__ void arrive_relaxed(unsigned int *bar, int p, bool ll) {
+    if (ll) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar + p) : "memory");
+    else phase_arrive(bar, p);
+}
+__device__ __forceinline__ void wait_relaxed(const unsigned int *bar, int p, unsigned int G, bool ll) {
+    if (!ll) { phase_wait(bar, p, G); return; }
     unsigned int v;
     do {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + p) : "memory");
@@ -110,10 +115,12 @@ __device__ __forceinline__ void load_xb(uint32_t xf_lane, int B, bool xact, uint
 }
 // One tile: 16 rows x 4 blocks.  acc0 / acc1: this lane's running sums for (row g, block column t) and (row g+8, t).
 // tile_lane = shared address of the tile + 16 * lane.
-__device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, const float corr_v, const uint32_t (&xb)[16], float &acc0, float &acc1) {
+__device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, uint32_t corr_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
     const uint4 wa4 = lds128(tile_lane);
     const uint4 wb4 = lds128(tile_lane + 512u);
     const uint32_t dd = lds32(d_lane);
+    float corr_v, pb;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(corr_v), "=f"(pb) : "r"(corr_addr));
     const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
     float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
@@ -127,8 +134,8 @@ __device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, co
     const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
     const float v0 = ((c[0] + e[0]) + (c[1] + e[1])) + corr_v;   // (hi + lo columns) - 8 * sum(x) of the block
     const float v1 = ((c[2] + e[2]) + (c[3] + e[3])) + corr_v;
-    acc0 = fmaf(df.x, v0, acc0);
-    acc1 = fmaf(df.y, v1, acc1);
+    acc0 = fmaf(df.x * pb, v0, acc0);
+    acc1 = fmaf(df.y * pb, v1, acc1);
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -149,6 +156,7 @@ struct AttnT {              // lives in the fragment buffer during the attention
     int is_last;
 };
 static_assert(sizeof(AttnT) <= TL_XFRAG_BYTES, "attention scratch must fit the fragment buffer");
+static_assert(TL_CW == 16, "the finishing warp sums 8 partials per half-warp");
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
     asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_u32(dst_smem)), "l"(src) : "memory");
@@ -174,12 +182,13 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
     }
 }
 
-__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, AttnT &S, int tid,
-                                                unsigned int want, unsigned int oflag) {
+// pre1: rows of the item's SECOND pass, fetched into registers before the grid barrier (same thread mapping as attn_fetch)
+__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, const float4 (&pre1)[4], AttnT &S,
+                                                int tid, unsigned int want, unsigned int oflag, bool ll, unsigned long long *trace) {
     constexpr int HD = 64, HALF = 32;
     const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
     const int warp = tid >> 5, lane = tid & 31;
-    const int kvh = I.kvh, n = pos + 1;
+    const int kvh = I.kvh;
     float *kc = at.kcache + (size_t)layer * at.seq_len * kvd, *vc = at.vcache + (size_t)layer * at.seq_len * kvd;
     const bool owner = pos >= I.t_begin && pos < I.t_end;   // exactly one split per kv head holds the new position
 
@@ -187,9 +196,9 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
     if (tid < (group + 1) * HALF) {
         const int hh = tid >> 5, i = tid & 31;
         const bool isk = hh == group;
-        // q | k | v are one flagged vector [H*hd + 2*kvd] (at.q = base; at.k / at.v are element offsets from it)
+        // q | k | v are one vector [H*hd + 2*kvd] (at.q = base; at.k / at.v are element offsets from it)
         const int e0 = isk ? (int)(at.k - at.q) + kvh * HD : (kvh * group + hh) * HD;
-        const float x0 = ld_ll_wait(at.q, e0 + i, want), x1 = ld_ll_wait(at.q, e0 + i + HALF, want);
+        const float x0 = ll ? ld_ll_wait(at.q, e0 + i, want) : __ldcg(at.q + e0 + i), x1 = ll ? ld_ll_wait(at.q, e0 + i + HALF, want) : __ldcg(at.q + e0 + i + HALF);
         const float c = __ldg(at.cos_t + (size_t)pos * HALF + i), sn = __ldg(at.sin_t + (size_t)pos * HALF + i);
         float r0, r1;
         if (!at.conj) { r0 = x0 * c - x1 * sn; r1 = x0 * sn + x1 * c; }
@@ -197,10 +206,12 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
         float *dst = isk ? S.knew : S.q[hh];
         dst[i] = r0; dst[i + HALF] = r1;
     } else if (tid >= TL_CONSUMERS - HD) {
-        S.vnew[tid - (TL_CONSUMERS - HD)] = ld_ll_wait(at.q, (int)(at.v - at.q) + kvh * HD + tid - (TL_CONSUMERS - HD), want);
+        const int ev = (int)(at.v - at.q) + kvh * HD + tid - (TL_CONSUMERS - HD);
+        S.vnew[tid - (TL_CONSUMERS - HD)] = ll ? ld_ll_wait(at.q, ev, want) : __ldcg(at.q + ev);
     }
     if (tid < group) { S.m_run[tid] = -INFINITY; S.l_run[tid] = 0.f; S.corr[tid] = 0.f; }
     tl_bar<TL_CONSUMERS>();
+    if (tid == 0 && trace) trace[5] = gtime();   // q / k / v in shared memory
     if (at.qk_norm) {
         if (warp <= group) {  // RMSNormBare, go/quant.go:584-594
             float *vec = warp == group ? S.knew : S.q[warp];
@@ -221,9 +232,21 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
     const int nparts = TL_CONSUMERS / gthreads;            // PV: positions interleaved over nparts thread sets
     const int part = tid / gthreads, rem = tid - part * gthreads, hh = rem >> 6, dd = rem & 63;
     float acc = 0.f;
-    for (int c0 = I.t_begin; c0 < I.t_end; c0 += TA_CH) {
+    int pass = 0;
+    for (int c0 = I.t_begin; c0 < I.t_end; c0 += TA_CH, pass++) {
         const int cn = min(TA_CH, I.t_end - c0);
-        if (!(prefetched && c0 == I.t_begin)) attn_fetch(kc, vc, kvd, kvh, c0, cn, pos, S, tid);
+        if (prefetched && pass == 1) {                      // second pass: the rows are waiting in registers
+#pragma unroll
+            for (int j = 0; j < 4; j++) {
+                const int idx = tid + j * TL_CONSUMERS, tl = idx >> 5, f = idx & 31;
+                if (tl < cn && c0 + tl < pos) {
+                    if (f < 16) *reinterpret_cast<float4 *>(&S.Ks[tl][4 * f]) = pre1[j];
+                    else *reinterpret_cast<float4 *>(&S.Vs[tl][4 * (f - 16)]) = pre1[j];
+                }
+            }
+        } else if (!(prefetched && pass == 0)) {
+            attn_fetch(kc, vc, kvd, kvh, c0, cn, pos, S, tid);
+        }
         if (owner && pos >= c0 && pos < c0 + cn) {          // the new position's row comes from this token's k / v
             if (tid < HD) S.Ks[pos - c0][tid] = S.knew[tid];
             else if (tid < 2 * HD) S.Vs[pos - c0][tid - HD] = S.vnew[tid - HD];
@@ -257,60 +280,68 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
             }
         }
         tl_bar<TL_CONSUMERS>();
-        if (part < nparts) {
-            float a = acc * S.corr[hh];
-            for (int tl = part; tl < cn; tl += nparts) a = fmaf(S.p[hh][tl], S.Vs[tl][dd], a);
-            acc = a;
+        if (part < nparts) {   // 4 independent chains over the positions of my part
+            float a0 = acc * S.corr[hh], a1 = 0.f, a2 = 0.f, a3 = 0.f;
+            int tl = part;
+            for (; tl + 3 * nparts < cn; tl += 4 * nparts) {
+                a0 = fmaf(S.p[hh][tl], S.Vs[tl][dd], a0);
+                a1 = fmaf(S.p[hh][tl + nparts], S.Vs[tl + nparts][dd], a1);
+                a2 = fmaf(S.p[hh][tl + 2 * nparts], S.Vs[tl + 2 * nparts][dd], a2);
+                a3 = fmaf(S.p[hh][tl + 3 * nparts], S.Vs[tl + 3 * nparts][dd], a3);
+            }
+            for (; tl < cn; tl += nparts) a0 = fmaf(S.p[hh][tl], S.Vs[tl][dd], a0);
+            acc = (a0 + a1) + (a2 + a3);
         }
         tl_bar<TL_CONSUMERS>();
     }
     S.pv[tid] = acc;
     tl_bar<TL_CONSUMERS>();
+    if (tid == 0 && trace) trace[6] = gtime();   // own positions done
     if (tid < gthreads) {
         float o = 0.f;
         for (int pp = 0; pp < nparts; pp++) o += S.pv[pp * gthreads + tid];
         const int h = kvh * group + hh;
-        if (I.nse == 1) {
-            st_ll(at.out, h * HD + dd, o * (1.0f / S.l_run[hh]), oflag);
-        } else {
-            at.part_acc[((size_t)(h * at.nsplit + I.sp)) * HD + dd] = o;
-            if (dd == 0) {
-                at.part_ml[(h * at.nsplit + I.sp) * 2] = S.m_run[hh];
-                at.part_ml[(h * at.nsplit + I.sp) * 2 + 1] = S.l_run[hh];
-            }
-        }
-    }
-    if (I.nse > 1) {
-        __threadfence();
-        tl_bar<TL_CONSUMERS>();
-        if (tid == 0) {
-            unsigned int old;
-            asm volatile("atom.acq_rel.gpu.global.add.u32 %0, [%1], 1;" : "=r"(old) : "l"(at.split_cnt + layer * at.n_kv_heads + kvh) : "memory");
-            S.is_last = (old == (unsigned)I.nse - 1u);
-        }
-        tl_bar<TL_CONSUMERS>();
-        if (S.is_last && tid < gthreads) {
-            const int h = kvh * group + hh;
-            float M = -INFINITY;
-            for (int s = 0; s < I.nse; s++) M = fmaxf(M, __ldcg(at.part_ml + (h * at.nsplit + s) * 2));
-            float den = 0.f, o = 0.f;
-            for (int s = 0; s < I.nse; s++) {
-                const float m = __ldcg(at.part_ml + (h * at.nsplit + s) * 2), l = __ldcg(at.part_ml + (h * at.nsplit + s) * 2 + 1);
-                if (l > 0.f) {
-                    const float wgt = expf(m - M);
-                    den = fmaf(wgt, l, den);
-                    o = fmaf(wgt, __ldcg(at.part_acc + ((size_t)(h * at.nsplit + s)) * HD + dd), o);
+        float M = S.m_run[hh], den = S.l_run[hh];
+        if (I.nse > 1) {
+            // un-normalised partials travel as flagged {value, flag} pairs: split 0 folds the others as they land (fixed order =>
+            // deterministic), no fence, no counter
+            const unsigned int pflag = oflag;
+            if (I.sp != 0) {
+                st_ll(at.part_acc, (h * at.nsplit + I.sp) * HD + dd, o, pflag);
+                if (dd < 2) st_ll(at.part_ml, (h * at.nsplit + I.sp) * 2 + dd, dd == 0 ? M : den, pflag);
+            } else {
+                float mo[MG_MAX_SPLIT], lo[MG_MAX_SPLIT];
+                float Mx = M;
+                for (int s = 1; s < I.nse; s++) {
+                    mo[s] = ld_ll_wait(at.part_ml, (h * at.nsplit + s) * 2, pflag);
+                    lo[s] = ld_ll_wait(at.part_ml, (h * at.nsplit + s) * 2 + 1, pflag);
+                    if (lo[s] > 0.f) Mx = fmaxf(Mx, mo[s]);
                 }
+                float w0 = den > 0.f ? expf(M - Mx) : 0.f;
+                float dsum = w0 * den, osum = w0 * o;
+                for (int s = 1; s < I.nse; s++) {
+                    const float pa = ld_ll_wait(at.part_acc, (h * at.nsplit + s) * HD + dd, pflag);
+                    if (lo[s] > 0.f) {
+                        const float wgt = expf(mo[s] - Mx);
+                        dsum = fmaf(wgt, lo[s], dsum);
+                        osum = fmaf(wgt, pa, osum);
+                    }
+                }
+                o = osum; den = dsum;
             }
-            st_ll(at.out, h * HD + dd, o * (1.0f / den), oflag);
+        }
+        if (I.nse == 1 || I.sp == 0) {
+            const float r = o * (1.0f / den);
+            if (ll) st_ll(at.out, h * HD + dd, r, oflag); else at.out[h * HD + dd] = r;
         }
     }
     tl_bar<TL_CONSUMERS>();  // S is reused by the next item of this CTA
+    if (tid == 0 && trace) trace[7] = gtime();   // outputs / partials stored
 }
 
 // Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Kept out of line so that its registers (two sets of B
 // fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
-// My two tiles of slot k are band tiles 32k + 2 warp (+1); their block group advances by 32 mod nbg per slot.
+// My tiles of slot k are band tiles TL_TS * k + tl_first(warp) (+1); their block group advances by TL_TS mod nbg per slot.
 __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, int warp, int lane, uint32_t ring_u, uint32_t xfrag_u,
                                         uint32_t corr_u, uint32_t full_u, uint32_t empty_u, uint32_t red_lane) {
     const int g = lane >> 2, t = lane & 3;
@@ -318,24 +349,25 @@ __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, i
     uint32_t xb0[16], xb1[16];             // B fragments of my two tiles (reloaded only when the block group changes)
 #pragma unroll
     for (int i = 0; i < 16; i++) { xb0[i] = 0u; xb1[i] = 0u; }
-    uint32_t tile_lane0 = ring_u + (uint32_t)(2 * warp) * TL_TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
-    uint32_t d_lane0 = ring_u + (uint32_t)(2 * warp) * TL_TILE + 1024u + (uint32_t)lane * 4u;
-    uint32_t xf_lane = xfrag_u + (uint32_t)g * 64u, corr_lane = corr_u + (uint32_t)t * 4u;
+    const int t0 = tl_first(warp), t1 = t0 + 1;   // my tiles of a slot
+    uint32_t tile_lane0 = ring_u + (uint32_t)t0 * TL_TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
+    uint32_t d_lane0 = ring_u + (uint32_t)t0 * TL_TILE + 1024u + (uint32_t)lane * 4u;
+    uint32_t xf_lane = xfrag_u + (uint32_t)g * 64u, corr_lane = corr_u + (uint32_t)t * 8u;
     asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(corr_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
-    int B = 2 * warp - rg_of(2 * warp, nbg, magic) * nbg;
+    int B = t0 - rg_of(t0, nbg, magic) * nbg;
     const int stepB = TL_TS - rg_of(TL_TS, nbg, magic) * nbg;
     int cb0 = -1, cb1 = -1;                // block groups whose fragments xb0 / xb1 hold
     for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
         const uint32_t slot = (uint32_t)it % TL_SLOTS;
         const int n = min(TL_TS, band - c0);
         mbar_wait_u(full_u + slot * 8u, ((uint32_t)it / TL_SLOTS) & 1u);
-        if (2 * warp < n) {
+        if (t0 < n) {
             const uint32_t so = slot * (uint32_t)TL_SLOT_BYTES, ro = red_lane + slot * (uint32_t)(TL_CW * 2 * 16 * 4);
             float acc0 = 0.f, acc1 = 0.f;
             if (B != cb0) { load_xb(xf_lane, B, xact, xb0); cb0 = B; }
-            tile_dot(tile_lane0 + so, d_lane0 + so, __uint_as_float(lds32(corr_lane + (uint32_t)B * 16u)), xb0, acc0, acc1);
+            tile_dot(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
             uint32_t eo = 0;
-            if (2 * warp + 1 < n) {
+            if (t1 != t0 && t1 < n) {
                 int B1 = B + 1;
                 if (B1 == nbg) {   // my second tile starts the next row group: flush the first
                     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
@@ -344,7 +376,7 @@ __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, i
                     acc0 = 0.f; acc1 = 0.f; B1 = 0; eo = 64u;
                 }
                 if (B1 != cb1) { load_xb(xf_lane, B1, xact, xb1); cb1 = B1; }
-                tile_dot(tile_lane0 + so + TL_TILE, d_lane0 + so + TL_TILE, __uint_as_float(lds32(corr_lane + (uint32_t)B1 * 16u)), xb1, acc0, acc1);
+                tile_dot(tile_lane0 + so + TL_TILE, d_lane0 + so + TL_TILE, corr_lane + (uint32_t)B1 * 32u, xb1, acc0, acc1);
             }
             acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
             acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
@@ -362,8 +394,6 @@ struct TlShared {
     uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
     float red[TL_SLOTS][TL_CW][2][16];
     double ss_red[TL_CW];
-    float mx_red[TL_CW];
-    float post_scale[2];
     TilePhase ph[2];
 };
 
@@ -372,12 +402,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     __shared__ TlShared sh;
     uint8_t *ring = smem;
     uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
-    float *corr = reinterpret_cast<float *>(xfrag + TL_XFRAG_BYTES);
+    float2 *corr = reinterpret_cast<float2 *>(xfrag + TL_XFRAG_BYTES);   // per block: {zero-point correction, 2^20 / S_b}
     AttnT &att = *reinterpret_cast<AttnT *>(xfrag);   // the attention phase has no GEMV input: same bytes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
     const unsigned int flag_base = (A.epoch ? __ldg(A.epoch) : 0u) * (unsigned)(A.n_phases + 1);
+    const bool ll = A.ll != 0;
     if (tid == 0) {
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -426,6 +457,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *resid_src = ldg_ptr(&P->resid);
             const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);
             const unsigned int oflag = flag_base + (unsigned)p + 1u;
+            const bool normed = ldg_ptr(&P->norm_w) != nullptr;
+            const int cols_p = __ldg(&P->cols);
             int u0, u1;
             band_of(__ldg(&P->n_rg) / urg, blockIdx.x, G, u0, u1);
             const int band = (u1 - u0) * urg * nbg;
@@ -444,15 +477,24 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r); }
                 }
                 mbar_wait(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
-                if (c0 == 0) post = sh.post_scale[p & 1];
+                if (lane == 0 && c1 == band) TL_TRACE(p, 5);   // last slot consumed by every math warp
+                if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607: inv = 1 / sqrt(ss / n + eps) from the float64 sum of squares
+                    double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);   // fixed butterfly order: deterministic
+                    // float64 sum like the reference; the final 1/sqrt in fp32 (within 1 ulp of the reference's float32(1/sqrt(float64)))
+                    post = rsqrtf((float)s2 * (1.0f / (float)cols_p) + A.eps);
+                }
                 for (int q = q_first; q <= q_last; q++) {
                     const int a = max(q * nbg, c0) - c0, b = min((q + 1) * nbg, c1) - c0;   // tiles [a, b) of this slot belong to row group q
-                    const int wa = a >> 1, wb = (b - 1) >> 1;
-                    float s = 0.f;
-                    for (int w = wa + half; w <= wb; w += 2) {
-                        const int e = (rg_of(c0 + 2 * w, nbg, magic) == q) ? 0 : 1;
-                        s += sh.red[slot][w][e][row];
+                    const int wa = tl_owner(a), wb = tl_owner(b - 1);
+                    // warp w dropped this row group's sums into entry 0, unless its first tile still belonged to the previous group
+                    // (then: entry 1); independent loads first, one fixed summation tree after (deterministic)
+                    float pv[TL_CW / 2];
+#pragma unroll
+                    for (int i = 0; i < TL_CW / 2; i++) {
+                        const int w = wa + half + 2 * i;
+                        pv[i] = (w <= wb) ? sh.red[slot][w][(w == wa && tl_first(w) < a) ? 1 : 0][row] : 0.f;
                     }
+                    float s = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
                     racc += s;
                     if ((q + 1) * nbg <= c1) {   // last tile of the row group is in this slot: publish its 16 rows
@@ -481,7 +523,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 if (lane == 0) mbar_arrive(&sh.free_bar[slot]);
             }
             __syncwarp();
-            if (lane == 0) { TL_TRACE(p, 4); arrive_relaxed(A.bar, p); }   // no fence: the outputs carry their own flags
+            if (lane == 0) { TL_TRACE(p, 4); arrive_relaxed(A.bar, p, ll); TL_TRACE(p, 6); }   // flagged outputs: no fence
             __syncwarp();
         }
         return;
@@ -515,25 +557,38 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (kind == PH_ATTN) {
             tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
             const int pos = *A.at.pos, n = pos + 1;
-            int nse = (n + TA_CH - 1) / TA_CH;
+            int nse = (n + 2 * TA_CH - 1) / (2 * TA_CH);   // up to two prefetched passes (2 x 64 positions) per split
             nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
             const int n_items = A.at.n_kv_heads * nse;
             const int kvd = A.at.n_kv_heads * 64;
             bool pre = false;
+            float4 pre1[4];
+#pragma unroll
+            for (int j = 0; j < 4; j++) pre1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
                 const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse);
-                attn_fetch(A.at.kcache + (size_t)layer * A.at.seq_len * kvd, A.at.vcache + (size_t)layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
-                           min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
+                const float *kc = A.at.kcache + (size_t)layer * A.at.seq_len * kvd, *vc = A.at.vcache + (size_t)layer * A.at.seq_len * kvd;
+                attn_fetch(kc, vc, kvd, I.kvh, I.t_begin, min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
+                const int t1 = I.t_begin + TA_CH;   // second pass -> registers
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    const int idx = tid + j * TL_CONSUMERS, tl = idx >> 5, f = idx & 31, t = t1 + tl;
+                    if (t < I.t_end && t < pos)
+                        pre1[j] = f < 16 ? __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + I.kvh * 64 + 4 * f))
+                                         : __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)t * kvd + I.kvh * 64 + 4 * (f - 16)));
+                }
                 pre = true;
             }
-            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G, ll); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u);
+                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, pre1, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u, ll,
+                                A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr);
                 pre = false;
             }
-            tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores (they carry their own flags; the KV rows are for later tokens)
-            if (tid == 0) { TL_TRACE(p, 3); arrive_relaxed(A.bar, p); TL_TRACE(p, 4); }
+            if (!ll) __threadfence();
+            tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores (flagged ones carry their own flags; the KV rows are for later tokens)
+            if (tid == 0) { TL_TRACE(p, 3); arrive_relaxed(A.bar, p, ll); TL_TRACE(p, 4); }
             continue;
         }
 
@@ -552,16 +607,22 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             }
         }
         if (p > 0) {
-            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G, ll); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
-        float xv[TL_MAX_ITEMS][8];
+        // One pass, no grid-wide reduction in front of the conversion: every 32-element block gets its own power-of-two scale S_b
+        // (max|y| * S_b in [2^10, 2^11), so 16 * y * S_b stays inside fp16 and the lo terms keep 10+ bits), applied back per block in
+        // tile_dot; the RMSNorm scale (one scalar per vector) is applied by the finishing warp to the finished sums:
+        // W . (inv * (x o w)) = inv * (W . (x o w)).  The float64 sum of squares is therefore off the critical path.
         double ss = 0.0;
-        float mx = 0.f;
 #pragma unroll
         for (int r = 0; r < TL_MAX_ITEMS; r++) {
-            const int q = tid + r * TL_CONSUMERS;
+            const int q = tid + r * TL_CONSUMERS;          // item q = elements [8q, 8q+8); whole warps agree on q < nitem_pad + 31
+            const bool store = q < nitem_pad;              // zero fragments for the padding blocks of the last block group
+            float y[8];
+#pragma unroll
+            for (int i = 0; i < 8; i++) y[i] = 0.f;
             if (q < nitem) {
                 if (in_ll) {   // 8 flagged elements = 64 bytes; look again until all eight carry this phase's input flag
                     const uint4 *src = reinterpret_cast<const uint4 *>(px) + 4 * q;
@@ -570,43 +631,27 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     do {
                         a0 = ld_vol_v4(src); a1 = ld_vol_v4(src + 1); a2 = ld_vol_v4(src + 2); a3 = ld_vol_v4(src + 3);
                     } while (a0.y != want || a0.w != want || a1.y != want || a1.w != want || a2.y != want || a2.w != want || a3.y != want || a3.w != want);
-                    xv[r][0] = __uint_as_float(a0.x); xv[r][1] = __uint_as_float(a0.z); xv[r][2] = __uint_as_float(a1.x); xv[r][3] = __uint_as_float(a1.z);
-                    xv[r][4] = __uint_as_float(a2.x); xv[r][5] = __uint_as_float(a2.z); xv[r][6] = __uint_as_float(a3.x); xv[r][7] = __uint_as_float(a3.z);
+                    y[0] = __uint_as_float(a0.x); y[1] = __uint_as_float(a0.z); y[2] = __uint_as_float(a1.x); y[3] = __uint_as_float(a1.z);
+                    y[4] = __uint_as_float(a2.x); y[5] = __uint_as_float(a2.z); y[6] = __uint_as_float(a3.x); y[7] = __uint_as_float(a3.z);
                 } else {
                     const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
-                    xv[r][0] = a.x; xv[r][1] = a.y; xv[r][2] = a.z; xv[r][3] = a.w; xv[r][4] = b.x; xv[r][5] = b.y; xv[r][6] = b.z; xv[r][7] = b.w;
+                    y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
                 }
-                float s4 = 0.f;
+                if (normed) {
+                    float s4 = 0.f;
 #pragma unroll
-                for (int i = 0; i < 8; i++) {
-                    if (normed) { s4 = fmaf(xv[r][i], xv[r][i], s4); mx = fmaxf(mx, fabsf(xv[r][i] * wv[r][i])); }
-                    else mx = fmaxf(mx, fabsf(xv[r][i]));
+                    for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= wv[r][i]; }
+                    ss += (double)s4;
                 }
-                ss += (double)s4;
             }
-        }
-        mx = warp_max(mx);
-        if (normed) ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
-        if (lane == 0) { sh.mx_red[warp] = mx; sh.ss_red[warp] = ss; }
-        tl_bar<TL_CONSUMERS>();
-        float inv = 1.f;
-        {
-            float m2 = 0.f;
-            double s2 = 0.0;
+            float mx = 0.f;
 #pragma unroll
-            for (int w = 0; w < TL_CW; w++) { m2 = fmaxf(m2, sh.mx_red[w]); s2 += sh.ss_red[w]; }
-            mx = m2;
-            if (normed) { inv = (float)(1.0 / sqrt(s2 / (double)cols + (double)A.eps)); mx *= inv; }
-        }
-        // power-of-two scale S: max|x| * S in [2^10, 2^11), so 16 * x * S stays inside fp16 and the lo terms keep 10+ bits
-        int es = 264 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-        es = es < 27 ? 27 : (es > 227 ? 227 : es);
-        const float S = __uint_as_float((uint32_t)es << 23);
-        if (tid == 0) sh.post_scale[p & 1] = __uint_as_float((uint32_t)(274 - es) << 23);   // 2^20 / S
-#pragma unroll
-        for (int r = 0; r < TL_MAX_ITEMS; r++) {
-            const int q = tid + r * TL_CONSUMERS;          // item q = elements [8q, 8q+8); whole warps agree on q < nitem_pad + 31
-            const bool store = q < nitem_pad;              // zero fragments for the padding blocks of the last block group
+            for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(y[i]));
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the four lanes of a block sit next to each other
+            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+            int es = 264 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+            es = es < 27 ? 27 : (es > 227 ? 227 : es);
+            const float S = __uint_as_float((uint32_t)es << 23);
             const int b = q >> 2, o = (q & 3) * 8;         // block, offset of my 8 elements inside it
             const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
             float bs = 0.f;
@@ -616,12 +661,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 float v[4];
 #pragma unroll
                 for (int j = 0; j < 4; j++) {
-                    float xx = 0.f;
-                    if (q < nitem) {
-                        xx = xv[r][4 * k + j];
-                        if (normed) xx = xx * inv * wv[r][4 * k + j];   // x * inv * w, go/quant.go:604-606
-                    }
-                    v[j] = xx * S;
+                    v[j] = y[4 * k + j] * S;
                     bs += v[j];
                     if (pos == 0) v[j] *= 16.f;
                 }
@@ -636,9 +676,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             }
             bs += __shfl_xor_sync(0xffffffffu, bs, 1);
             bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-            if (store && (q & 3) == 0) corr[b] = -7.62939453125e-6f * bs;   // -8 * 2^-20 * sum(x * S) over the block
+            // per block: -8 * 2^-20 * sum(y * S_b) (the zero point) and 2^20 / S_b (undoes the operand scaling)
+            if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)(274 - es) << 23));
         }
-        tl_bar<TL_CONSUMERS>();
+        if (normed) {
+            ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
+            if (lane == 0) sh.ss_red[warp] = ss;
+        }
+        tl_bar<TL_CONSUMERS>();   // fragments complete; the finishing warp turns ss_red into the RMSNorm scale once the first slot is consumed
         if (tid == 0) TL_TRACE(p, 2);
 
         // ---- stream the band ----

@@ -38,13 +38,18 @@ constexpr int TL_CW = 16;                          // math warps
 constexpr int TL_CONSUMERS = TL_CW * 32;           // 512
 constexpr int TL_THREADS = TL_CONSUMERS + 64;      // + copy warp + finishing warp
 constexpr int TL_TILE = 1152;                      // bytes per tile (16 rows x 4 blocks of Q4_0)
-constexpr int TL_TS = 2 * TL_CW;                   // tiles per ring slot: two per math warp
+constexpr int TL_TS = 2 * TL_CW;                   // tiles per ring slot: two per math warp (a 31-tile slot that relieves the math warp
+                                                   // next to the finishing warp was measured 15 % slower: slots stop lining up with the
+                                                   // 32-tile row groups of 4096-column matrices, so fragments are reloaded every slot)
 constexpr int TL_SLOT_BYTES = TL_TS * TL_TILE;     // 36,864
+// first tile of math warp w inside a slot, and the warp that owns slot tile j
+__host__ __device__ constexpr int tl_first(int w) { return 2 * w; }
+__host__ __device__ constexpr int tl_owner(int j) { return j >> 1; }
 constexpr int TL_SLOTS = 4;
 constexpr int TL_MAX_NBG = 96;                     // block groups per row: cols <= 12,288
 constexpr int TL_XFRAG_BYTES = TL_MAX_NBG * 512;   // fp16 hi/lo fragments of the phase input
 constexpr int TL_MAX_ITEMS = 3;                    // 8-float items per math thread in the prologue
-constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_MAX_NBG * 4 * 4;
+constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_MAX_NBG * 4 * 8;
 
 enum { TEPI_STORE = 0, TEPI_RESID = 1, TEPI_SWIGLU = 2 };
 
@@ -70,7 +75,8 @@ struct TileArgs {
     const TilePhase *phases;
     int n_phases;
     unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
-    const unsigned int *epoch;  // launch counter behind the flags of the flagged activation vectors (null: no flagged vectors)
+    const unsigned int *epoch;  // launch counter behind the flags of flagged {value, flag} vectors (attention partials; activations when ll)
+    int ll;                   // 1: activation vectors are flagged pairs and the grid barriers carry no fence
     MegaAttn at;
     float eps;
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
