@@ -1,3 +1,4 @@
-timeout 600 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 300 -k "matmul_vs_oracle or forward_logits or greedy_stream or tier_greedy" > gpurun_out/pytest_quick.log 2>&1; echo "quick rc=$?"; tail -3 gpurun_out/pytest_quick.log
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "wide_tier or long_context or matmul_vs_oracle or forward_logits or greedy_stream or tier_greedy" > gpurun_out/pytest_quick.log 2>&1; echo "quick rc=$?"; tail -5 gpurun_out/pytest_quick.log
+timeout 120 python tools/gemv_bench.py --rows 96000 --cols 4096 2>&1 | tail -1
 timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'], d['roofline']['kernel_alone'])"
 NL_TRACE=gpurun_out/trace_tiled.bin timeout 300 python bench.py --steps 1 --warmup 1 --no-cpu-baseline 2>&1 | tail -1 | cut -c1-100

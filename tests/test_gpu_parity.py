@@ -309,6 +309,56 @@ def test_tier_greedy_256_identical(tier, typ, n_new):
     m.close()
 
 
+@pytest.mark.parametrize("tier,layers,vocab", [("large", 2, 8192), ("big", 1, 4096), ("goldie", 2, 4096)])
+def test_wide_tier_logits_vs_oracle(tier, layers, vocab):
+    """Full-width layers of the big tiers (more 16-row groups than SMs in every projection, so every band edge of the persistent
+    decode kernel cuts a row group / gate-up pair): logits against the oracle over a few positions, then determinism."""
+    gf = T.SyntheticGGUF(tier, G.GGML_Q4_0, seed=3, seq_len=160, vocab=vocab, layers=layers)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(9)
+    toks = np.concatenate([[1], rng.integers(3, vocab, size=5)]).astype(np.int32)
+    for pos, t in enumerate(toks):
+        m.forward(int(t), pos)
+        exp = o.forward(int(t), pos)
+        assert maxrel(m.state.logits, exp) < 2e-5
+        assert int(np.argmax(m.state.logits)) == int(np.argmax(exp))
+    last = m.state.logits.copy()
+    # long context: several attention splits whose partials are folded across CTAs (GPU only: determinism + finiteness,
+    # plus agreement of the final logits with a replay)
+    seq = rng.integers(3, vocab, size=150).astype(np.int32)
+    m.reset()
+    for pos, t in enumerate(seq):
+        m.forward(int(t), pos)
+    a = m.state.logits.copy()
+    m.reset()
+    for pos, t in enumerate(seq):
+        m.forward(int(t), pos)
+    assert np.array_equal(a, m.state.logits) and np.isfinite(a).all()
+    m.reset()
+    for pos, t in enumerate(toks):
+        m.forward(int(t), pos)
+    assert np.array_equal(last, m.state.logits)
+    m.close(); o.close()
+
+
+def test_long_context_attention_vs_oracle():
+    """mini Q4_0 at positions past 128 / 256: the attention phase runs 2-3 splits per kv head with a second pass per split."""
+    gf = T.SyntheticGGUF("mini", G.GGML_Q4_0, seed=2, seq_len=320, vocab=2048)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(4)
+    seq = rng.integers(3, 2048, size=300).astype(np.int32)
+    for pos, t in enumerate(seq):
+        exp = o.forward(int(t), pos)
+        if pos in (0, 63, 64, 127, 128, 129, 191, 192, 255, 256, 257, 299):
+            m.forward(int(t), pos)
+            assert maxrel(m.state.logits, exp) < 2e-5, pos
+        else:
+            m.forward(int(t), pos)
+    m.close(); o.close()
+
+
 # ---------------------------------------------------------------- tensor parallel (needs >= 2 GPUs on the box)
 def test_tensor_parallel_2gpu_parity():
     import socket
