@@ -237,7 +237,8 @@ def main():
         e2e_s = float(t.item())
     e2e_value = n_seq * tps * e2e_steps / e2e_s
 
-    # ---- roofline of the dominant kernel family (the dequant-fused streaming GEMV: >95 % of the step, profiles/r01_launches_big.md) ----
+    # ---- roofline of the dominant kernel (decode_tiled_kernel: one launch per token, >99 % of the step, profiles/r01_launches_big_decode.md;
+    #      models the tiled path does not take fall back to the gemv_stream_kernel chain and report that family instead) ----
     # achieved = algorithmic bytes of one decode step (weights + one embedding row + norm weights + KV read/write at
     # the mid position of the step) / CUDA-event time of that step, i.e. every launch gap, the attention and the argmax kernels are
     # charged to the GEMV too -- a lower bound of the kernel's own bandwidth.  The kernel alone, back to back on the largest
@@ -260,11 +261,20 @@ def main():
         dm.close()
     except Exception as e:  # never let the extra measurement kill the bench line
         alone = {"error": str(e)}
-    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": None,
+    traffic = None
+    try:   # measured DRAM bytes per launch of the dominant kernel from the committed ncu capture (one launch = one decoded token)
+        tr = json.load(open(os.path.join(ROOT, "profiles", "r01_traffic.json")))
+        traffic = tr.get(decode_path, {}).get(f"{args.tier}/{args.dtype}", {}).get("dram_bytes_per_launch")
+    except Exception:
+        traffic = None
+    roofline = {"bound": "hbm", "achieved": achieved, "peak": peak, "unit": "GB/s", "frac": achieved / peak, "traffic": traffic,
                 "peak_source": peak_src, "kernel": decode_path,
                 "bytes_per_step": int(bytes_tok), "gemv_share_of_bytes": weight_only / bytes_tok, "kernel_alone": alone,
-                "how": "algorithmic bytes per decode step / CUDA-event time per step (lower bound of the kernel's bandwidth); "
-                       "kernel_alone = LM-head GEMV timed back to back on L2-cold replicas"}
+                "launch_us": 1000.0 * ms_per_step / tps,
+                "how": "one launch of the persistent kernel = one decoded token: algorithmic bytes per token (SURVEY 8d, mid position of the "
+                       "step) / CUDA-event time per token over the timed region (embedding, argmax and memset nodes, <1 % of the step, are "
+                       "charged to it); traffic = ncu dram bytes per launch (profiles/r01_traffic.json); kernel_alone = the same kernel "
+                       "as a one-phase LM-head GEMV timed back to back on L2-cold replicas"}
 
     out = {"metric": metric, "value": value, "unit": "tok/s", "n_gpus": world, "steps": args.steps, "warmup": args.warmup,
            "ms_per_step": ms_per_step, "higher_is_better": True, "scaling": "strong" if tp > 1 else "weak", "vs_baseline": None, "dtype": "f32",

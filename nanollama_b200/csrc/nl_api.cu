@@ -273,6 +273,7 @@ struct nl_model {
     // flagged {value, flag} activation vectors of the tiled path: residual stream, q | k | v, attention output, SwiGLU output
     uint2 *x_ll = nullptr, *qkv_ll = nullptr, *ao_ll = nullptr, *hb_ll = nullptr;
     unsigned int *d_epoch = nullptr;    // launch counter behind the flags
+    float2 *amax = nullptr; bool amax_valid = false;   // per-CTA argmax pairs of the LM-head phase
     float *qkv_bias = nullptr;
     TilePhase *d_tphases = nullptr; TileArgs targs; int tile_grid = 0;
     int act_stride = 0;          // floats between the MG_REPS copies of x / xb2 / hb (replica 0 is what every other path uses)
@@ -453,6 +454,8 @@ static int build_tiled(nl_model *m) {
         for (auto &b : ll) { NL_CUDA(cudaMalloc(b.p, (size_t)b.n * 8)); NL_CUDA(cudaMemset(*b.p, 0, (size_t)b.n * 8)); }
         NL_CUDA(cudaMalloc(&m->d_epoch, 4));
         NL_CUDA(cudaMemset(m->d_epoch, 0, 4));
+        NL_CUDA(cudaMalloc(&m->amax, (size_t)G * 8));
+        NL_CUDA(cudaMemset(m->amax, 0, (size_t)G * 8));
     }
     if (any_bias) {   // q | k | v biases in the same order as the concatenated rows (absent ones are zero)
         NL_CUDA(cudaMalloc(&m->qkv_bias, (size_t)c.n_layers * nqkv * 4));
@@ -519,7 +522,7 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)c.n_heads * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.ll = LL;
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.ll = LL; a.amax = m->amax; m->amax_valid = true;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
@@ -640,7 +643,9 @@ static int record_forward(nl_model *m, int batch) {
 
 static int record_advance(nl_model *m, int batch) {
     StepState s{m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->gen_cap};
-    argmax_advance_kernel<<<batch, 1024, 0, m->st>>>(m->logits, m->c.vocab_size, s);
+    // batch 1 on the tiled path: the LM-head phase of the previous forward left one (max, index) pair per CTA
+    if (batch == 1 && m->tile_ok && m->amax_valid) argmax_pairs_advance_kernel<<<1, 32, 0, m->st>>>(m->amax, m->tile_grid, s);
+    else argmax_advance_kernel<<<batch, 1024, 0, m->st>>>(m->logits, m->c.vocab_size, s);
     NL_CUDA(cudaGetLastError());
     return NL_OK;
 }
@@ -937,7 +942,7 @@ void nl_destroy(nl_model *m) {
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
-    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch}) if (q) cudaFree(q);
+    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch, (void *)m->amax}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
     if (m->d_tphases) cudaFree(m->d_tphases);
     if (m->d_phases) cudaFree(m->d_phases);

@@ -373,6 +373,28 @@ static __global__ void __launch_bounds__(1024) argmax_advance_kernel(const float
         }
     }
 }
+// same step when the persistent decode kernel has already left one (maximum, first index) pair per CTA (nl_tile.cu): n pairs, one warp
+static __global__ void __launch_bounds__(32) argmax_pairs_advance_kernel(const float2 *__restrict__ pairs, int n, StepState st) {
+    float best = -INFINITY; int bi = 0x7fffffff;
+    for (int i = threadIdx.x; i < n; i += 32) {
+        const float2 pr = pairs[i];
+        const float v = pr.x; const int vi = __float_as_int(pr.y);
+        if (v > best || (v == best && vi < bi)) { best = v; bi = vi; }
+    }
+#pragma unroll
+    for (int o = 16; o > 0; o >>= 1) {
+        float ov = __shfl_xor_sync(0xffffffffu, best, o); int oi = __shfl_xor_sync(0xffffffffu, bi, o);
+        if (ov > best || (ov == best && oi < bi)) { best = ov; bi = oi; }
+    }
+    if (threadIdx.x == 0) {
+        if (bi == 0x7fffffff) bi = 0;  // all -inf / NaN: Go's loop would keep index 0
+        const int g = st.gen_count[0];
+        if (g < st.gen_cap) st.gen[g] = bi;
+        st.token[0] = bi;
+        st.pos[0] += 1;
+        st.gen_count[0] = g + 1;
+    }
+}
 // prefill feed: token <- prompt[i], pos <- i for sequence 0
 static __global__ void feed_prompt_kernel(const int32_t *__restrict__ prompt, int32_t *cursor, int32_t pos0, int32_t *token, int32_t *pos) {
     const int i = *cursor;

@@ -144,18 +144,19 @@ __device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, ui
 // q / k / v; after the barrier one round trip brings q, k, v, everything else is on chip.  Short contexts use one split per
 // 64 positions (a single split writes the final output directly, no cross-CTA combine); longer ones use up to at.nsplit splits
 // whose un-normalised partials (flash-decoding) are folded by the split that arrives last (fixed order => deterministic).
-constexpr int TA_CH = 64;   // positions per pass
+constexpr int TA_CH = 96;   // positions per pass (one pass per item up to 9 x 96 positions of context)
 struct AttnT {              // lives in the fragment buffer during the attention phase
     float q[MG_MAX_GROUP][64];
     float knew[64], vnew[64];
     float p[MG_MAX_GROUP][TA_CH];
-    float Ks[TA_CH][68];    // 272-byte rows: 16-byte aligned, and 8 consecutive rows hit 8 different bank groups
+    float Ks[TA_CH][68];    // 272-byte rows: 16-byte aligned, and 8 consecutive rows hit 8 different bank groups (reused for the
+                            // per-thread PV partials once the last pass is over: TL_CONSUMERS * 4 floats)
     float Vs[TA_CH][64];
-    float pv[TL_CONSUMERS];
     float m_run[MG_MAX_GROUP], l_run[MG_MAX_GROUP], corr[MG_MAX_GROUP];
     int is_last;
 };
 static_assert(sizeof(AttnT) <= TL_XFRAG_BYTES, "attention scratch must fit the fragment buffer");
+static_assert(TA_CH * 68 >= TL_CONSUMERS * 4 && TA_CH <= 96, "PV partials alias the K rows; the softmax step covers 3 x 32 positions");
 static_assert(TL_CW == 16, "the finishing warp sums 8 partials per half-warp");
 
 __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
@@ -182,8 +183,7 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
     }
 }
 
-// pre1: rows of the item's SECOND pass, fetched into registers before the grid barrier (same thread mapping as attn_fetch)
-__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, const float4 (&pre1)[4], AttnT &S,
+__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, AttnT &S,
                                                 int tid, unsigned int want, unsigned int oflag, bool ll, unsigned long long *trace) {
     constexpr int HD = 64, HALF = 32;
     const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
@@ -228,50 +228,47 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
         vc[(size_t)pos * kvd + kvh * HD + tid] = S.vnew[tid];
     }
 
-    const int gthreads = group * HD;                       // one thread per (head of the group, dim | position)
-    const int nparts = TL_CONSUMERS / gthreads;            // PV: positions interleaved over nparts thread sets
-    const int part = tid / gthreads, rem = tid - part * gthreads, hh = rem >> 6, dd = rem & 63;
-    float acc = 0.f;
+    const int gthreads = group * HD;                       // epilogue: one thread per (head of the group, dim)
+    const int pthreads = group * 16;                       // PV: one thread per (head, 4 dims), positions interleaved over nparts thread sets
+    const int nparts = TL_CONSUMERS / pthreads;
+    const int part = tid / pthreads, prem = tid - part * pthreads, hh = prem >> 4, quad = prem & 15;
+    float4 acc4 = make_float4(0.f, 0.f, 0.f, 0.f);
     int pass = 0;
     for (int c0 = I.t_begin; c0 < I.t_end; c0 += TA_CH, pass++) {
         const int cn = min(TA_CH, I.t_end - c0);
-        if (prefetched && pass == 1) {                      // second pass: the rows are waiting in registers
-#pragma unroll
-            for (int j = 0; j < 4; j++) {
-                const int idx = tid + j * TL_CONSUMERS, tl = idx >> 5, f = idx & 31;
-                if (tl < cn && c0 + tl < pos) {
-                    if (f < 16) *reinterpret_cast<float4 *>(&S.Ks[tl][4 * f]) = pre1[j];
-                    else *reinterpret_cast<float4 *>(&S.Vs[tl][4 * (f - 16)]) = pre1[j];
-                }
-            }
-        } else if (!(prefetched && pass == 0)) {
-            attn_fetch(kc, vc, kvd, kvh, c0, cn, pos, S, tid);
-        }
+        if (!(prefetched && pass == 0)) attn_fetch(kc, vc, kvd, kvh, c0, cn, pos, S, tid);
         if (owner && pos >= c0 && pos < c0 + cn) {          // the new position's row comes from this token's k / v
             if (tid < HD) S.Ks[pos - c0][tid] = S.knew[tid];
             else if (tid < 2 * HD) S.Vs[pos - c0][tid - HD] = S.vnew[tid - HD];
         }
         cp_async_wait_all();
         tl_bar<TL_CONSUMERS>();
-        if (tid < gthreads && dd < cn) {                    // scores: thread = (head hh, position dd)
-            const float4 *kp = reinterpret_cast<const float4 *>(&S.Ks[dd][0]), *qp = reinterpret_cast<const float4 *>(&S.q[hh][0]);
-            float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
-#pragma unroll
-            for (int j = 0; j < 16; j++) {
-                const float4 kk = kp[j], qq = qp[j];
-                d0 = fmaf(qq.x, kk.x, d0); d1 = fmaf(qq.y, kk.y, d1); d2 = fmaf(qq.z, kk.z, d2); d3 = fmaf(qq.w, kk.w, d3);
+        {   // scores: 8 threads per position, each with 8 of the 64 dims (two conflict-free 16-byte columns), for every head of the group
+            const int sub = tid & 7;
+            for (int tl = tid >> 3; tl < TA_CH; tl += TL_CONSUMERS / 8) {   // whole warps agree on tl < TA_CH
+                float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
+                if (tl < cn) { k0 = *reinterpret_cast<const float4 *>(&S.Ks[tl][4 * sub]); k1 = *reinterpret_cast<const float4 *>(&S.Ks[tl][32 + 4 * sub]); }
+                for (int h2 = 0; h2 < group; h2++) {
+                    const float4 q0 = *reinterpret_cast<const float4 *>(&S.q[h2][4 * sub]), q1 = *reinterpret_cast<const float4 *>(&S.q[h2][32 + 4 * sub]);
+                    float d = (fmaf(q0.x, k0.x, q0.y * k0.y) + fmaf(q0.z, k0.z, q0.w * k0.w)) + (fmaf(q1.x, k1.x, q1.y * k1.y) + fmaf(q1.z, k1.z, q1.w * k1.w));
+                    d += __shfl_xor_sync(0xffffffffu, d, 1);
+                    d += __shfl_xor_sync(0xffffffffu, d, 2);
+                    d += __shfl_xor_sync(0xffffffffu, d, 4);
+                    if (sub == 0 && tl < cn) S.p[h2][tl] = d * at.scale;
+                }
             }
-            S.p[hh][dd] = ((d0 + d1) + (d2 + d3)) * at.scale;
         }
         tl_bar<TL_CONSUMERS>();
         if (warp < group) {  // running softmax statistics of head `warp` (flash-decoding form of go/quant.go:610-626)
             const float s0 = lane < cn ? S.p[warp][lane] : -INFINITY, s1 = lane + 32 < cn ? S.p[warp][lane + 32] : -INFINITY;
-            const float mx = warp_max(fmaxf(s0, s1));
+            const float s2 = lane + 64 < cn ? S.p[warp][lane + 64] : -INFINITY;
+            const float mx = warp_max(fmaxf(fmaxf(s0, s1), s2));
             const float m_old = S.m_run[warp], m_new = fmaxf(m_old, mx);
-            const float e0 = lane < cn ? expf(s0 - m_new) : 0.f, e1 = lane + 32 < cn ? expf(s1 - m_new) : 0.f;
+            const float e0 = lane < cn ? expf(s0 - m_new) : 0.f, e1 = lane + 32 < cn ? expf(s1 - m_new) : 0.f, e2 = lane + 64 < cn ? expf(s2 - m_new) : 0.f;
             if (lane < cn) S.p[warp][lane] = e0;
             if (lane + 32 < cn) S.p[warp][lane + 32] = e1;
-            const float sum = warp_sum(e0 + e1);
+            if (lane + 64 < cn) S.p[warp][lane + 64] = e2;
+            const float sum = warp_sum((e0 + e1) + e2);
             if (lane == 0) {
                 const float corr = (m_old == -INFINITY) ? 0.f : expf(m_old - m_new);
                 S.corr[warp] = corr;
@@ -280,26 +277,27 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
             }
         }
         tl_bar<TL_CONSUMERS>();
-        if (part < nparts) {   // 4 independent chains over the positions of my part
-            float a0 = acc * S.corr[hh], a1 = 0.f, a2 = 0.f, a3 = 0.f;
-            int tl = part;
-            for (; tl + 3 * nparts < cn; tl += 4 * nparts) {
-                a0 = fmaf(S.p[hh][tl], S.Vs[tl][dd], a0);
-                a1 = fmaf(S.p[hh][tl + nparts], S.Vs[tl + nparts][dd], a1);
-                a2 = fmaf(S.p[hh][tl + 2 * nparts], S.Vs[tl + 2 * nparts][dd], a2);
-                a3 = fmaf(S.p[hh][tl + 3 * nparts], S.Vs[tl + 3 * nparts][dd], a3);
+        if (part < nparts) {   // PV: thread = (part of the positions, head, 4 dims)
+            const float cr = S.corr[hh];
+            float4 a = make_float4(acc4.x * cr, acc4.y * cr, acc4.z * cr, acc4.w * cr);
+            for (int tl = part; tl < cn; tl += nparts) {
+                const float pw = S.p[hh][tl];
+                const float4 v = *reinterpret_cast<const float4 *>(&S.Vs[tl][4 * quad]);
+                a.x = fmaf(pw, v.x, a.x); a.y = fmaf(pw, v.y, a.y); a.z = fmaf(pw, v.z, a.z); a.w = fmaf(pw, v.w, a.w);
             }
-            for (; tl < cn; tl += nparts) a0 = fmaf(S.p[hh][tl], S.Vs[tl][dd], a0);
-            acc = (a0 + a1) + (a2 + a3);
+            acc4 = a;
         }
         tl_bar<TL_CONSUMERS>();
+        if (tid == 0 && trace && pass == 0) trace[2] = gtime();   // first pass done
     }
-    S.pv[tid] = acc;
+    float *pvs = &S.Ks[0][0];   // every pass is over (the loop ends on a barrier): the K rows become the PV partials
+    *reinterpret_cast<float4 *>(&pvs[tid * 4]) = acc4;
     tl_bar<TL_CONSUMERS>();
     if (tid == 0 && trace) trace[6] = gtime();   // own positions done
     if (tid < gthreads) {
+        const int hh = tid >> 6, dd = tid & 63;            // (shadows the PV mapping)
         float o = 0.f;
-        for (int pp = 0; pp < nparts; pp++) o += S.pv[pp * gthreads + tid];
+        for (int pp = 0; pp < nparts; pp++) o += pvs[(pp * pthreads + hh * 16 + (dd >> 2)) * 4 + (dd & 3)];
         const int h = kvh * group + hh;
         float M = S.m_run[hh], den = S.l_run[hh];
         if (I.nse > 1) {
@@ -464,6 +462,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const int band = (u1 - u0) * urg * nbg;
             const int rg0 = u0 * urg;
             float racc = 0.f, gate = 0.f, post = 1.f;
+            float best = -INFINITY;
+            int best_i = 0x7fffffff;
             for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
                 const int slot = it % TL_SLOTS;
                 const int c1 = min(c0 + TL_TS, band);
@@ -515,12 +515,22 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                                 if (bias) v += __ldg(bias + r);
                                 if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
                                 if (out_ll) st_ll(out, r, v, oflag); else out[r] = v;
+                                if (v > best || (v == best && r < best_i)) { best = v; best_i = r; }   // first maximum, go/main.go:400-408
                             }
                         }
                     }
                 }
                 __syncwarp();
                 if (lane == 0) mbar_arrive(&sh.free_bar[slot]);
+            }
+            if (A.amax && p == A.n_phases - 1) {   // LM head: this CTA's (maximum, first index) for the greedy step that follows
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+                    const float ov = __shfl_xor_sync(0xffffffffu, best, o);
+                    const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
+                    if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
+                }
+                if (lane == 0) A.amax[blockIdx.x] = make_float2(best, __int_as_float(best_i));
             }
             __syncwarp();
             if (lane == 0) { TL_TRACE(p, 4); arrive_relaxed(A.bar, p, ll); TL_TRACE(p, 6); }   // flagged outputs: no fence
@@ -557,32 +567,21 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (kind == PH_ATTN) {
             tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
             const int pos = *A.at.pos, n = pos + 1;
-            int nse = (n + 2 * TA_CH - 1) / (2 * TA_CH);   // up to two prefetched passes (2 x 64 positions) per split
+            int nse = (n + TA_CH - 1) / TA_CH;   // one prefetched pass (up to 96 positions) per split while the splits last
             nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
             const int n_items = A.at.n_kv_heads * nse;
             const int kvd = A.at.n_kv_heads * 64;
             bool pre = false;
-            float4 pre1[4];
-#pragma unroll
-            for (int j = 0; j < 4; j++) pre1[j] = make_float4(0.f, 0.f, 0.f, 0.f);
             if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
                 const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse);
-                const float *kc = A.at.kcache + (size_t)layer * A.at.seq_len * kvd, *vc = A.at.vcache + (size_t)layer * A.at.seq_len * kvd;
-                attn_fetch(kc, vc, kvd, I.kvh, I.t_begin, min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
-                const int t1 = I.t_begin + TA_CH;   // second pass -> registers
-#pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    const int idx = tid + j * TL_CONSUMERS, tl = idx >> 5, f = idx & 31, t = t1 + tl;
-                    if (t < I.t_end && t < pos)
-                        pre1[j] = f < 16 ? __ldcg(reinterpret_cast<const float4 *>(kc + (size_t)t * kvd + I.kvh * 64 + 4 * f))
-                                         : __ldcg(reinterpret_cast<const float4 *>(vc + (size_t)t * kvd + I.kvh * 64 + 4 * (f - 16)));
-                }
+                attn_fetch(A.at.kcache + (size_t)layer * A.at.seq_len * kvd, A.at.vcache + (size_t)layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
+                           min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
                 pre = true;
             }
             if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G, ll); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, pre1, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u, ll,
+                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u, ll,
                                 A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr);
                 pre = false;
             }

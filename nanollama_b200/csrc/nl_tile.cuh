@@ -47,7 +47,8 @@ __host__ __device__ constexpr int tl_first(int w) { return 2 * w; }
 __host__ __device__ constexpr int tl_owner(int j) { return j >> 1; }
 constexpr int TL_SLOTS = 4;
 constexpr int TL_MAX_NBG = 96;                     // block groups per row: cols <= 12,288
-constexpr int TL_XFRAG_BYTES = TL_MAX_NBG * 512;   // fp16 hi/lo fragments of the phase input
+constexpr int TL_XFRAG_BYTES = 57344;              // fp16 hi/lo fragments of the phase input (TL_MAX_NBG * 512 = 48 KB); the attention
+                                                   // phase reuses the buffer and needs 56 KB for 96 cached K/V rows
 constexpr int TL_MAX_ITEMS = 3;                    // 8-float items per math thread in the prologue
 constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_MAX_NBG * 4 * 8;
 
@@ -76,6 +77,7 @@ struct TileArgs {
     int n_phases;
     unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
     const unsigned int *epoch;  // launch counter behind the flags of flagged {value, flag} vectors (attention partials; activations when ll)
+    float2 *amax;             // optional [grid]: per CTA (maximum, index as int bits) of the last phase's outputs (device-side greedy)
     int ll;                   // 1: activation vectors are flagged pairs and the grid barriers carry no fence
     MegaAttn at;
     float eps;

@@ -31,7 +31,8 @@ def main(path):
                   np.nanmean(a - c), np.nanmax(a - c),          # finish + publish
                   np.nanmean(w1 - w0),                          # time spent waiting at the barrier (idle)
                   np.nanmean(t[:, p, 5] - w1), np.nanmean(t[:, p, 6] - t[:, p, 5]), np.nanmean(t[:, p, 7] - t[:, p, 6]),   # attention: inputs, own positions, combine
-                  np.nanmean(t[:, p, 5] - c), np.nanmean(a - t[:, p, 5]), np.nanmean(t[:, p, 6] - a)])   # GEMV finisher: all warps done, sums+stores, fence+arrive
+                  np.nanmean(t[:, p, 5] - c), np.nanmean(a - t[:, p, 5]), np.nanmean(t[:, p, 6] - a),   # GEMV finisher: all warps done, sums+stores, fence+arrive
+                  np.nanmean(f - t[:, p, 5])])                    # attention: first pass (stamp 2 - stamp 5)
     print(f"grid {G}, phases {P}; token span {(end[-1] - np.nanmin(t[:, 0, 2])) / 1e3:.1f} us (from first fragments of phase 0)")
     print("| phase | n | duration us | barrier seen after last arrive | prologue mean/max | consume mean/max | finish mean/max | idle at barrier mean |")
     print("|---|---|---|---|---|---|---|---|")
@@ -44,7 +45,7 @@ def main(path):
         tot += np.nansum(a[:, 0])
         print(f"| {k} | {len(a)} | {m[0]:.2f} | {m[1]:.2f} | {m[2]:.2f} / {m[3]:.2f} | {m[4]:.2f} / {m[5]:.2f} | {m[6]:.2f} / {m[7]:.2f} | {m[8]:.2f} |", end="")
         if k == "attn":
-            print(f"  [attention: q/k/v in smem {m[9]:.2f}, own positions {m[10]:.2f}, fold+store {m[11]:.2f}]")
+            print(f"  [attention: q/k/v in smem {m[9]:.2f}, own positions {m[10]:.2f} (first pass {m[15]:.2f}), fold+store {m[11]:.2f}]")
         else:
             print(f"  [finisher: last warp after tid0 {m[12]:.2f}, sums+stores {m[13]:.2f}, fence+arrive {m[14]:.2f}]")
     print(f"sum of phase durations: {tot:.1f} us")
