@@ -268,7 +268,7 @@ struct nl_model {
     unsigned long long *d_trace = nullptr;
     int mega_reps = 1;
     // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
-    bool tile_ok = false;
+    bool tile_ok = false; int tile_type = NL_Q4_0;
     std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
     // flagged {value, flag} activation vectors of the tiled path: residual stream, q | k | v, attention output, SwiGLU output
     uint2 *x_ll = nullptr, *qkv_ll = nullptr, *ao_ll = nullptr, *hb_ll = nullptr;
@@ -405,7 +405,7 @@ static int build_mega(nl_model *m) {
 
 // ---- tiled tensor-core decode path (nl_tile.cuh) ----
 static bool tile_eligible(const DevMat &w) {
-    return w.type == NL_Q4_0 && w.rows % 16 == 0 && w.cols % 32 == 0 && w.cols <= (int64_t)TL_MAX_NBG * 128 && w.rows * (w.cols / 32) < (1ll << 31);
+    return (w.type == NL_Q4_0 || w.type == NL_Q8_0) && w.rows % 16 == 0 && w.cols % 32 == 0 && w.cols <= (int64_t)TL_MAX_NBG * 128 && w.rows * (w.cols / 32) < (1ll << 31);
 }
 // Builds one tiled matrix from `n` planar matrices of equal cols: concatenated row-wise (interleave = false) or with their
 // 16-row groups interleaved (gate/up: group i of mats[0], group i of mats[1], ...).
@@ -413,11 +413,11 @@ static int make_tiles(uint8_t **dst, const DevMat *const *mats, int n, bool inte
     const int nb = (int)(mats[0]->cols / 32), nbg = (nb + 3) / 4;
     int64_t n_rg = 0;
     for (int i = 0; i < n; i++) n_rg += mats[i]->rows / 16;
-    NL_CUDA(cudaMalloc(dst, (size_t)n_rg * nbg * TL_TILE));
+    NL_CUDA(cudaMalloc(dst, (size_t)n_rg * nbg * tile_bytes(mats[0]->type)));
     int off = 0;
     for (int i = 0; i < n; i++) {
         const DevMat &w = *mats[i];
-        if (launch_tile_q4_0(w.qs, w.d, (int)w.rows, nb, *dst, nbg, interleave ? i : off, interleave ? n : 1, st)) return fail(NL_ERR_CUDA, "tile repack launch failed");
+        if (launch_tile_repack(w.type, w.qs, w.d, (int)w.rows, nb, *dst, nbg, interleave ? i : off, interleave ? n : 1, st)) return fail(NL_ERR_CUDA, "tile repack launch failed");
         off += (int)(w.rows / 16);
     }
     return NL_OK;
@@ -441,9 +441,10 @@ static int build_tiled(nl_model *m) {
     if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
     const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
     if (!tile_eligible(outw)) return NL_OK;
+    const int wtype = outw.type;   // one kernel instantiation per model: every matrix must be of this type
     bool any_bias = false;
     for (const Layer &ly : m->L) {
-        for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown}) if (!tile_eligible(*w)) return NL_OK;
+        for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown}) if (!tile_eligible(*w) || w->type != wtype) return NL_OK;
         if (ly.bq || ly.bk || ly.bv) any_bias = true;
     }
     const int G = m->opts.num_sms;
@@ -534,7 +535,7 @@ static int build_tiled(nl_model *m) {
         NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
         a.trace = m->d_trace;
     }
-    m->tile_grid = G;
+    m->tile_grid = G; m->tile_type = wtype;
     m->tile_ok = true;
     return NL_OK;
 }
@@ -556,7 +557,7 @@ static int record_forward(nl_model *m, int batch) {
         NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
         bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
         launches++;
-        if (launch_tiled(m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (launch_tiled(m->tile_type, m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         launches++;
         NL_CUDA(cudaGetLastError());
         m->launches_fwd = launches;
@@ -1231,7 +1232,7 @@ static int matrix_tiled_gemv(nl_matrix *w, int idx) {
     TileArgs a; memset(&a, 0, sizeof a);
     a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar; a.inflight = tile_inflight();
     const int units = (int)(w->copies[0].rows / 16);
-    if (launch_tiled(a, units < w->opts.num_sms ? units : w->opts.num_sms, w->st)) return fail(NL_ERR_CUDA, "tiled gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (launch_tiled(w->copies[0].type, a, units < w->opts.num_sms ? units : w->opts.num_sms, w->st)) return fail(NL_ERR_CUDA, "tiled gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return NL_OK;
 }
 

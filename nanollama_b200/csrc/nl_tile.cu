@@ -27,6 +27,32 @@ __global__ void tile_q4_0_kernel(const uint4 *__restrict__ qs, const __half *__r
     reinterpret_cast<uint32_t *>(dst + 1024)[lane] = (uint32_t)d0 | ((uint32_t)d1 << 16);
 }
 
+__global__ void tile_q8_0_kernel(const uint4 *__restrict__ qs, const __half *__restrict__ d, int rows, int nb, uint8_t *__restrict__ tiles,
+                                 int nbg, int rg_off, int rg_stride, int n_rg_src) {
+    constexpr int TILE = TileCfg<NL_Q8_0>::TILE;
+    const long long gid = (long long)blockIdx.x * blockDim.x + threadIdx.x;
+    const int lane = (int)(gid & 31);
+    const long long tile = gid >> 5;
+    if (tile >= (long long)n_rg_src * nbg) return;
+    const int R = (int)(tile / nbg), B = (int)(tile % nbg);
+    const int g = lane >> 2, t = lane & 3;
+    const int blk = 4 * B + t;
+    uint8_t *dst = tiles + ((size_t)(rg_off + R * rg_stride) * nbg + B) * TILE;
+    const uint4 z = make_uint4(0, 0, 0, 0);
+    uint4 a0 = z, a1 = z, b0 = z, b1 = z;
+    unsigned short d0 = 0, d1 = 0;
+    const int r0 = 16 * R + g, r1 = r0 + 8;
+    if (blk < nb) {
+        if (r0 < rows) { a0 = qs[((size_t)r0 * nb + blk) * 2]; a1 = qs[((size_t)r0 * nb + blk) * 2 + 1]; d0 = __half_as_ushort(d[(size_t)r0 * nb + blk]); }
+        if (r1 < rows) { b0 = qs[((size_t)r1 * nb + blk) * 2]; b1 = qs[((size_t)r1 * nb + blk) * 2 + 1]; d1 = __half_as_ushort(d[(size_t)r1 * nb + blk]); }
+    }
+    reinterpret_cast<uint4 *>(dst)[lane] = a0;
+    reinterpret_cast<uint4 *>(dst + 512)[lane] = a1;
+    reinterpret_cast<uint4 *>(dst + 1024)[lane] = b0;
+    reinterpret_cast<uint4 *>(dst + 1536)[lane] = b1;
+    reinterpret_cast<uint32_t *>(dst + 2048)[lane] = (uint32_t)d0 | ((uint32_t)d1 << 16);
+}
+
 // ---- device helpers ----
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
     asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
@@ -133,6 +159,28 @@ __device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, ui
     }
     const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
     const float v0 = ((c[0] + e[0]) + (c[1] + e[1])) + corr_v;   // (hi + lo columns) - 8 * sum(x) of the block
+    const float v1 = ((c[2] + e[2]) + (c[3] + e[3])) + corr_v;
+    acc0 = fmaf(df.x * pb, v0, acc0);
+    acc1 = fmaf(df.y * pb, v1, acc1);
+}
+
+// Q8_0 tile: eight MMAs, each on word i (elements 4i..4i+3) of the lane's block; B fragment registers 2i, 2i+1.
+__device__ __forceinline__ void tile_dot_q8(uint32_t tile_lane, uint32_t d_lane, uint32_t corr_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
+    const uint4 a_lo = lds128(tile_lane), a_hi = lds128(tile_lane + 512u), b_lo = lds128(tile_lane + 1024u), b_hi = lds128(tile_lane + 1536u);
+    const uint32_t dd = lds32(d_lane);
+    float corr_v, pb;
+    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(corr_v), "=f"(pb) : "r"(corr_addr));
+    const uint32_t wa[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
+    const uint32_t wb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
+    float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+#pragma unroll
+    for (int i = 0; i < 8; i++) {
+        const uint32_t ua = wa[i] ^ 0x80808080u, ub = wb[i] ^ 0x80808080u;   // int8 -> q + 128 in every byte
+        if (i & 1) mma_f16(e, ua & 0x00FF00FFu, ub & 0x00FF00FFu, (ua >> 8) & 0x00FF00FFu, (ub >> 8) & 0x00FF00FFu, xb[2 * i], xb[2 * i + 1]);
+        else mma_f16(c, ua & 0x00FF00FFu, ub & 0x00FF00FFu, (ua >> 8) & 0x00FF00FFu, (ub >> 8) & 0x00FF00FFu, xb[2 * i], xb[2 * i + 1]);
+    }
+    const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
+    const float v0 = ((c[0] + e[0]) + (c[1] + e[1])) + corr_v;   // (hi + lo columns) - 128 * sum(x) of the block
     const float v1 = ((c[2] + e[2]) + (c[3] + e[3])) + corr_v;
     acc0 = fmaf(df.x * pb, v0, acc0);
     acc1 = fmaf(df.y * pb, v1, acc1);
@@ -339,33 +387,36 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
 
 // Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Kept out of line so that its registers (two sets of B
 // fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
-// My tiles of slot k are band tiles TL_TS * k + tl_first(warp) (+1); their block group advances by TL_TS mod nbg per slot.
+// My tiles of slot k are band tiles TS * k + TPW * warp (+1 when TPW == 2); their block group advances by TS mod nbg per slot.
+template <int TYPE>
 __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, int warp, int lane, uint32_t ring_u, uint32_t xfrag_u,
                                         uint32_t corr_u, uint32_t full_u, uint32_t empty_u, uint32_t red_lane) {
+    constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW, D_OFF = TileCfg<TYPE>::D_OFF;
     const int g = lane >> 2, t = lane & 3;
     const bool xact = (t == (g >> 1));     // lane that holds B column g (block column g>>1, hi|lo = g&1)
     uint32_t xb0[16], xb1[16];             // B fragments of my two tiles (reloaded only when the block group changes)
 #pragma unroll
     for (int i = 0; i < 16; i++) { xb0[i] = 0u; xb1[i] = 0u; }
-    const int t0 = tl_first(warp), t1 = t0 + 1;   // my tiles of a slot
-    uint32_t tile_lane0 = ring_u + (uint32_t)t0 * TL_TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
-    uint32_t d_lane0 = ring_u + (uint32_t)t0 * TL_TILE + 1024u + (uint32_t)lane * 4u;
+    const int t0 = TPW * warp, t1 = t0 + 1;   // my tiles of a slot (t1 only when TPW == 2)
+    uint32_t tile_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
+    uint32_t d_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)D_OFF + (uint32_t)lane * 4u;
     uint32_t xf_lane = xfrag_u + (uint32_t)g * 64u, corr_lane = corr_u + (uint32_t)t * 8u;
     asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(corr_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
     int B = t0 - rg_of(t0, nbg, magic) * nbg;
-    const int stepB = TL_TS - rg_of(TL_TS, nbg, magic) * nbg;
+    const int stepB = TS - rg_of(TS, nbg, magic) * nbg;
     int cb0 = -1, cb1 = -1;                // block groups whose fragments xb0 / xb1 hold
-    for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
+    for (int c0 = 0; c0 < band; c0 += TS, it++) {
         const uint32_t slot = (uint32_t)it % TL_SLOTS;
-        const int n = min(TL_TS, band - c0);
+        const int n = min(TS, band - c0);
         mbar_wait_u(full_u + slot * 8u, ((uint32_t)it / TL_SLOTS) & 1u);
         if (t0 < n) {
             const uint32_t so = slot * (uint32_t)TL_SLOT_BYTES, ro = red_lane + slot * (uint32_t)(TL_CW * 2 * 16 * 4);
             float acc0 = 0.f, acc1 = 0.f;
             if (B != cb0) { load_xb(xf_lane, B, xact, xb0); cb0 = B; }
-            tile_dot(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
+            if constexpr (TYPE == NL_Q8_0) tile_dot_q8(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
+            else tile_dot(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
             uint32_t eo = 0;
-            if (t1 != t0 && t1 < n) {
+            if (TPW == 2 && t1 < n) {
                 int B1 = B + 1;
                 if (B1 == nbg) {   // my second tile starts the next row group: flush the first
                     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
@@ -374,7 +425,7 @@ __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, i
                     acc0 = 0.f; acc1 = 0.f; B1 = 0; eo = 64u;
                 }
                 if (B1 != cb1) { load_xb(xf_lane, B1, xact, xb1); cb1 = B1; }
-                tile_dot(tile_lane0 + so + TL_TILE, d_lane0 + so + TL_TILE, corr_lane + (uint32_t)B1 * 32u, xb1, acc0, acc1);
+                tile_dot(tile_lane0 + so + TILE, d_lane0 + so + TILE, corr_lane + (uint32_t)B1 * 32u, xb1, acc0, acc1);
             }
             acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
             acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
@@ -395,7 +446,9 @@ struct TlShared {
     TilePhase ph[2];
 };
 
+template <int TYPE>
 __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileArgs A) {
+    constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW;
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ TlShared sh;
     uint8_t *ring = smem;
@@ -426,16 +479,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             int u0, u1;
             band_of(__ldg(&P->n_rg) / urg, blockIdx.x, G, u0, u1);
             const int band = (u1 - u0) * urg * nbg;
-            const uint8_t *src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TL_TILE;
-            for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
+            const uint8_t *src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TILE;
+            for (int c0 = 0; c0 < band; c0 += TS, it++) {
                 const int slot = it % TL_SLOTS;
                 if (it >= TL_SLOTS) mbar_wait(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
                 // at most `inflight` copies on the wire: bytes requested but not yet landed are queue in front of every other
                 // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
                 if (it >= A.inflight) mbar_wait(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
-                const uint32_t bytes = (uint32_t)min(TL_TS, band - c0) * TL_TILE;
+                const uint32_t bytes = (uint32_t)min(TS, band - c0) * TILE;
                 mbar_expect_tx(&sh.full_bar[slot], bytes);
-                bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)c0 * TL_TILE, bytes, &sh.full_bar[slot], policy);
+                bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)c0 * TILE, bytes, &sh.full_bar[slot], policy);
             }
         }
         return;
@@ -464,9 +517,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             float racc = 0.f, gate = 0.f, post = 1.f;
             float best = -INFINITY;
             int best_i = 0x7fffffff;
-            for (int c0 = 0; c0 < band; c0 += TL_TS, it++) {
+            for (int c0 = 0; c0 < band; c0 += TS, it++) {
                 const int slot = it % TL_SLOTS;
-                const int c1 = min(c0 + TL_TS, band);
+                const int c1 = min(c0 + TS, band);
                 const int q_first = rg_of(c0, nbg, magic), q_last = rg_of(c1 - 1, nbg, magic);
                 // the residual of a row group that completes in this slot is fetched before we block on the math warps (not for the first
                 // slot of a phase: only a consumed slot proves that this CTA is past the grid barrier that orders the residual's writers)
@@ -485,14 +538,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 }
                 for (int q = q_first; q <= q_last; q++) {
                     const int a = max(q * nbg, c0) - c0, b = min((q + 1) * nbg, c1) - c0;   // tiles [a, b) of this slot belong to row group q
-                    const int wa = tl_owner(a), wb = tl_owner(b - 1);
+                    const int wa = a / TPW, wb = (b - 1) / TPW;   // math warp w owns slot tiles [TPW * w, TPW * w + TPW)
                     // warp w dropped this row group's sums into entry 0, unless its first tile still belonged to the previous group
                     // (then: entry 1); independent loads first, one fixed summation tree after (deterministic)
                     float pv[TL_CW / 2];
 #pragma unroll
                     for (int i = 0; i < TL_CW / 2; i++) {
                         const int w = wa + half + 2 * i;
-                        pv[i] = (w <= wb) ? sh.red[slot][w][(w == wa && tl_first(w) < a) ? 1 : 0][row] : 0.f;
+                        pv[i] = (w <= wb) ? sh.red[slot][w][(w == wa && TPW * w < a) ? 1 : 0][row] : 0.f;
                     }
                     float s = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
@@ -648,35 +701,55 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(y[i]));
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the four lanes of a block sit next to each other
             mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            int es = 264 - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+            // Q4_0: max|y| * S in [2^10, 2^11) (the low-nibble operands carry 16 * y * S); Q8_0: [2^14, 2^15)
+            int es = (TYPE == NL_Q8_0 ? 268 : 264) - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
             es = es < 27 ? 27 : (es > 227 ? 227 : es);
             const float S = __uint_as_float((uint32_t)es << 23);
             const int b = q >> 2, o = (q & 3) * 8;         // block, offset of my 8 elements inside it
-            const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
             float bs = 0.f;
             uint8_t *fb = xfrag + (size_t)(b >> 2) * 512 + (size_t)(2 * (b & 3)) * 64;
+            if constexpr (TYPE == NL_Q8_0) {
+                // MMA i takes elements 4i..4i+3: registers 2i = (e0, e2), 2i+1 = (e1, e3); my 8 elements fill registers o/2 .. o/2+3
+                float v[8];
 #pragma unroll
-            for (int k = 0; k < 2; k++) {
-                float v[4];
+                for (int j = 0; j < 8; j++) { v[j] = y[j] * S; bs += v[j]; }
+                uint32_t h[4], l[4];
 #pragma unroll
-                for (int j = 0; j < 4; j++) {
-                    v[j] = y[4 * k + j] * S;
-                    bs += v[j];
-                    if (pos == 0) v[j] *= 16.f;
+                for (int k = 0; k < 2; k++) {
+                    h[2 * k] = pack_h2(v[4 * k], v[4 * k + 2]); h[2 * k + 1] = pack_h2(v[4 * k + 1], v[4 * k + 3]);
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k])), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k + 1]));
+                    l[2 * k] = pack_h2(v[4 * k] - f0.x, v[4 * k + 2] - f0.y); l[2 * k + 1] = pack_h2(v[4 * k + 1] - f1.x, v[4 * k + 3] - f1.y);
                 }
-                const uint32_t h0 = pack_h2(v[0], v[2]), h1 = pack_h2(v[1], v[3]);
-                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h1));
-                const uint32_t l0 = pack_h2(v[0] - f0.x, v[2] - f0.y), l1 = pack_h2(v[1] - f1.x, v[3] - f1.y);
-                const int reg = 4 * (ib + k) + 2 * pos;
                 if (store) {
-                    *reinterpret_cast<uint2 *>(fb + reg * 4) = make_uint2(h0, h1);         // hi column of this block
-                    *reinterpret_cast<uint2 *>(fb + 64 + reg * 4) = make_uint2(l0, l1);    // lo column
+                    *reinterpret_cast<uint4 *>(fb + o * 2) = make_uint4(h[0], h[1], h[2], h[3]);          // hi column of this block
+                    *reinterpret_cast<uint4 *>(fb + 64 + o * 2) = make_uint4(l[0], l[1], l[2], l[3]);     // lo column
+                }
+            } else {
+                const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
+#pragma unroll
+                for (int k = 0; k < 2; k++) {
+                    float v[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        v[j] = y[4 * k + j] * S;
+                        bs += v[j];
+                        if (pos == 0) v[j] *= 16.f;
+                    }
+                    const uint32_t h0 = pack_h2(v[0], v[2]), h1 = pack_h2(v[1], v[3]);
+                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h1));
+                    const uint32_t l0 = pack_h2(v[0] - f0.x, v[2] - f0.y), l1 = pack_h2(v[1] - f1.x, v[3] - f1.y);
+                    const int reg = 4 * (ib + k) + 2 * pos;
+                    if (store) {
+                        *reinterpret_cast<uint2 *>(fb + reg * 4) = make_uint2(h0, h1);         // hi column of this block
+                        *reinterpret_cast<uint2 *>(fb + 64 + reg * 4) = make_uint2(l0, l1);    // lo column
+                    }
                 }
             }
             bs += __shfl_xor_sync(0xffffffffu, bs, 1);
             bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-            // per block: -8 * 2^-20 * sum(y * S_b) (the zero point) and 2^20 / S_b (undoes the operand scaling)
-            if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)(274 - es) << 23));
+            // per block: -zero_point * 2^-k * sum(y * S_b) (Q4_0: 8 * 2^-20, Q8_0: 128 * 2^-24 -- both 2^-17) and 2^k / S_b, which undoes
+            // the operand scaling (k = 20 | 24)
+            if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23));
         }
         if (normed) {
             ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
@@ -686,16 +759,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (tid == 0) TL_TRACE(p, 2);
 
         // ---- stream the band ----
-        it = stream_band(band, nbg, magic, it, warp, lane, smem_u32(ring), smem_u32(xfrag), smem_u32(corr), smem_u32(&sh.full_bar[0]),
+        it = stream_band<TYPE>(band, nbg, magic, it, warp, lane, smem_u32(ring), smem_u32(xfrag), smem_u32(corr), smem_u32(&sh.full_bar[0]),
                          smem_u32(&sh.empty_bar[0]), smem_u32(&sh.red[0][warp][0][lane >> 2]));
         if (tid == 0) TL_TRACE(p, 3);
     }
 }
 
-int launch_tiled(const TileArgs &a, int grid, cudaStream_t st) {
+template <int TYPE>
+static int launch_tiled_t(const TileArgs &a, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(decode_tiled_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
         configured = true;
     }
     cudaLaunchConfig_t cfg{};
@@ -704,14 +778,18 @@ int launch_tiled(const TileArgs &a, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they spin on each other
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel, a) == cudaSuccess ? 0 : -2;
+    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel<TYPE>, a) == cudaSuccess ? 0 : -2;
+}
+int launch_tiled(int type, const TileArgs &a, int grid, cudaStream_t st) {
+    return type == NL_Q8_0 ? launch_tiled_t<NL_Q8_0>(a, grid, st) : launch_tiled_t<NL_Q4_0>(a, grid, st);
 }
 
-
-int launch_tile_q4_0(const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st) {
+int launch_tile_repack(int type, const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st) {
     const int n_rg_src = (rows + 15) / 16;
     const long long threads = (long long)n_rg_src * nbg * 32;
-    tile_q4_0_kernel<<<(unsigned)((threads + 255) / 256), 256, 0, st>>>(reinterpret_cast<const uint4 *>(qs), d, rows, nb, tiles, nbg, rg_off, rg_stride, n_rg_src);
+    const unsigned grid = (unsigned)((threads + 255) / 256);
+    if (type == NL_Q8_0) tile_q8_0_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(qs), d, rows, nb, tiles, nbg, rg_off, rg_stride, n_rg_src);
+    else tile_q4_0_kernel<<<grid, 256, 0, st>>>(reinterpret_cast<const uint4 *>(qs), d, rows, nb, tiles, nbg, rg_off, rg_stride, n_rg_src);
     return cudaGetLastError() == cudaSuccess ? 0 : -2;
 }
 

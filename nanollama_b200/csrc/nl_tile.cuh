@@ -37,14 +37,20 @@ namespace nl {
 constexpr int TL_CW = 16;                          // math warps
 constexpr int TL_CONSUMERS = TL_CW * 32;           // 512
 constexpr int TL_THREADS = TL_CONSUMERS + 64;      // + copy warp + finishing warp
-constexpr int TL_TILE = 1152;                      // bytes per tile (16 rows x 4 blocks of Q4_0)
+constexpr int TL_TILE = 1152;                      // bytes per Q4_0 tile (16 rows x 4 blocks)
+// per weight type: tile bytes, tiles per math warp and ring slot, offset of the scale pairs inside a tile.
+// Q8_0 tile (2176 B): 4 planes of 512 B (rows g bytes 0-15 | rows g bytes 16-31 | rows g+8 bytes 0-15 | rows g+8 bytes 16-31, 16 B per
+// lane each: conflict-free LDS.128), then 32 x (fp16 d(row g), fp16 d(row g+8)).  An int8 XOR 0x80 in the low byte of a half is
+// the fp16 subnormal (q + 128) x 2^-24: 0.75 ALU ops per weight, the +128 goes into the same per-block correction as Q4_0's 8.
+template <int TYPE> struct TileCfg;
+template <> struct TileCfg<NL_Q4_0> { static constexpr int TILE = 1152, TPW = 2, D_OFF = 1024; };
+template <> struct TileCfg<NL_Q8_0> { static constexpr int TILE = 2176, TPW = 1, D_OFF = 2048; };
+inline int tile_bytes(int type) { return type == NL_Q8_0 ? TileCfg<NL_Q8_0>::TILE : TileCfg<NL_Q4_0>::TILE; }
 constexpr int TL_TS = 2 * TL_CW;                   // tiles per ring slot: two per math warp (a 31-tile slot that relieves the math warp
                                                    // next to the finishing warp was measured 15 % slower: slots stop lining up with the
                                                    // 32-tile row groups of 4096-column matrices, so fragments are reloaded every slot)
 constexpr int TL_SLOT_BYTES = TL_TS * TL_TILE;     // 36,864
-// first tile of math warp w inside a slot, and the warp that owns slot tile j
-__host__ __device__ constexpr int tl_first(int w) { return 2 * w; }
-__host__ __device__ constexpr int tl_owner(int j) { return j >> 1; }
+
 constexpr int TL_SLOTS = 4;
 constexpr int TL_MAX_NBG = 96;                     // block groups per row: cols <= 12,288
 constexpr int TL_XFRAG_BYTES = 57344;              // fp16 hi/lo fragments of the phase input (TL_MAX_NBG * 512 = 48 KB); the attention
@@ -87,8 +93,8 @@ struct TileArgs {
 
 // planar (qs, d) -> tiles: row group R of the source lands at tile row group rg_off + R * rg_stride (gate/up interleave: stride 2,
 // offsets 0 / 1; q,k,v concatenation: stride 1, running offsets).  Rows / blocks beyond the matrix become zero blocks (d = 0).
-int launch_tile_q4_0(const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st);
-int launch_tiled(const TileArgs &a, int grid, cudaStream_t st);
+int launch_tile_repack(int type, const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st);
+int launch_tiled(int type, const TileArgs &a, int grid, cudaStream_t st);
 inline int tile_inflight() {
     const char *e = getenv("NL_TILE_INFLIGHT");
     int k = e ? atoi(e) : TL_SLOTS;
