@@ -437,9 +437,11 @@ __global__ void bump_epoch_kernel(unsigned int *epoch) { *epoch += 1; }
 static int build_tiled(nl_model *m) {
     const nl_config &c = m->c;
     m->tile_ok = false;
-    if (getenv("NL_NO_TILED") || getenv("NL_MEGA") || m->tp > 1) return NL_OK;
+    if (getenv("NL_NO_TILED") || getenv("NL_MEGA")) return NL_OK;
+    const bool tpar = m->tp > 1;   // tensor parallel: the shards are tiled; o / down exchange their partials inside the kernel
+    if (tpar && (getenv("NL_NO_TILED_TP") || !m->tp_ready)) return NL_OK;
     if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
-    const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
+    const DevMat &outw = tpar ? m->lm_view : (m->output.present() ? m->output : m->tok_embd);
     if (!tile_eligible(outw)) return NL_OK;
     const int wtype = outw.type;   // one kernel instantiation per model: every matrix must be of this type
     bool any_bias = false;
@@ -448,7 +450,9 @@ static int build_tiled(nl_model *m) {
         if (ly.bq || ly.bk || ly.bv) any_bias = true;
     }
     const int G = m->opts.num_sms;
-    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size, nqkv = qdim + 2 * kvd;
+    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = m->ffn, nqkv = qdim + 2 * kvd;   // this rank's shard sizes
+    const int lvocab = tpar ? m->lvocab : c.vocab_size;
+    if (G > 256 || 5 * c.n_layers + 1 > 1024) return NL_OK;   // window areas of the tensor-parallel exchange
     cudaStream_t st = m->st;
     {
         struct { uint2 **p; int n; } ll[4] = {{&m->x_ll, dim}, {&m->qkv_ll, nqkv}, {&m->ao_ll, qdim}, {&m->hb_ll, ffn}};
@@ -475,8 +479,15 @@ static int build_tiled(nl_model *m) {
     // default: plain fp32 vectors (the pair buffers are then used as plain arrays) behind release / acquire barriers.
     // NL_TILE_LL=1: flagged {value, flag} vectors with fence-free barriers -- measured slower on B200 (the arrival overtakes the
     // data, the first look fails and costs a second L2 round trip; 2x the bytes per phase input), kept for experiments
-    const int LL = (getenv("NL_TILE_LL") && atoi(getenv("NL_TILE_LL")) == 1) ? 1 : 0;
+    const int LL = (!tpar && getenv("NL_TILE_LL") && atoi(getenv("NL_TILE_LL")) == 1) ? 1 : 0;
     void *xres = LL ? (void *)m->x_ll : (void *)m->x;
+    // tensor parallel: exchange e (o-projection of layer l: e = 2l, down-projection: e = 2l + 1) uses parity e & 1 of the exchange area;
+    // its consumer adds the ranks' partials to the residual before it (the embedding for e = 0, else xres2[(e - 1) & 1]) and leaves
+    // the sum in xres2[e & 1]
+    float *xres2[2] = {reinterpret_cast<float *>(m->x_ll), reinterpret_cast<float *>(m->x_ll) + dim};   // 2 x dim floats fit the pair buffer
+    auto consume_exchange = [&](TilePhase &Q, int e) {
+        Q.in_exch = 1; Q.par = e & 1; Q.prev = e == 0 ? m->x : xres2[(e - 1) & 1]; Q.next = xres2[e & 1];
+    };
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
         uint8_t *t_qkv = nullptr, *t_o = nullptr, *t_gu = nullptr, *t_dn = nullptr;
@@ -492,13 +503,21 @@ static int build_tiled(nl_model *m) {
         // layer 0 reads the embedding kernel's plain x; from then on the residual stream lives in x_ll
         const void *x_in = (l == 0 || !LL) ? (const void *)m->x : (const void *)m->x_ll;
         tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, LL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv_ll, LL);
+        if (tpar && l > 0) consume_exchange(P, 2 * l - 1);
         ph.push_back(P);
         memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
-        tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
+        if (tpar) {
+            tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, m->ao_ll, 0, nullptr, ly.bo, nullptr, 0);
+            P.exch_out = 1; P.par = 0; P.cross = 1;
+        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
         ph.push_back(P);
         tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, LL, ly.ffn_norm, nullptr, m->hb_ll, LL);
+        if (tpar) consume_exchange(P, 2 * l);
         ph.push_back(P);
-        tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, LL, nullptr, nullptr, xres, LL, xres, LL);
+        if (tpar) {
+            tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, m->hb_ll, 0, nullptr, nullptr, nullptr, 0);
+            P.exch_out = 1; P.par = 1; P.cross = 1;
+        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, LL, nullptr, nullptr, xres, LL, xres, LL);
         ph.push_back(P);
     }
     {
@@ -506,28 +525,35 @@ static int build_tiled(nl_model *m) {
         const DevMat *lm[1] = {&outw};
         if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_lm);
-        tile_gemv_phase(P, t_lm, c.vocab_size / 16, dim, 1, c.vocab_size, TEPI_STORE, xres, LL, m->output_norm, nullptr, m->logits, 0);
+        tile_gemv_phase(P, t_lm, lvocab / 16, dim, 1, lvocab, TEPI_STORE, xres, LL, m->output_norm, nullptr, m->logits, 0);
+        if (tpar) { consume_exchange(P, 2 * c.n_layers - 1); P.cross = 1; }   // vocab shard -> every rank's full logits vector
         ph.push_back(P);
     }
+    for (size_t i = 1; i < ph.size(); i++) ph[i].wait_cross = ph[i - 1].cross;
     NL_CUDA(cudaStreamSynchronize(st));
-    int nsplit = G / c.n_kv_heads;
+    int nsplit = G / m->nKV;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
     NL_CUDA(cudaMalloc(&m->d_tphases, ph.size() * sizeof(TilePhase)));
     NL_CUDA(cudaMemcpy(m->d_tphases, ph.data(), ph.size() * sizeof(TilePhase), cudaMemcpyHostToDevice));
     const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
     NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
-    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 8));   // flagged pairs
-    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 8));
-    NL_CUDA(cudaMemset(m->part_acc, 0, (size_t)c.n_heads * nsplit * 64 * 8));
-    NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)c.n_heads * nsplit * 2 * 8));
+    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)m->nH * nsplit * 64 * 8));   // flagged pairs
+    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)m->nH * nsplit * 2 * 8));
+    NL_CUDA(cudaMemset(m->part_acc, 0, (size_t)m->nH * nsplit * 64 * 8));
+    NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)m->nH * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
     a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.ll = LL; a.amax = m->amax; m->amax_valid = true;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
-    a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
+    a.at.n_heads = m->nH; a.at.n_kv_heads = m->nKV; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
+    if (tpar) {   // barrier counters, exchange area, logits and argmax pairs live in the IPC window every peer can write
+        a.tp = m->tp; a.rank = m->rank; a.dim = dim; a.lvocab = lvocab; a.peers = m->tp_peers;
+        a.ar_off = m->tp_lay.ar_data; a.bar_off = m->tp_lay.tile_bar; a.lg_off = m->tp_lay.lg_data; a.amax_off = m->tp_lay.tile_amax;
+        a.bar = reinterpret_cast<unsigned int *>(m->tp_win + m->tp_lay.tile_bar);
+    }
     a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_ll); a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
     a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
@@ -554,7 +580,8 @@ static int record_forward(nl_model *m, int batch) {
     }
     if (batch == 1 && m->tile_ok) {
         // everything after the embedding in ONE persistent tensor-core kernel (nl_tile.cuh); its grid-barrier counters start at zero
-        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
+        // (tensor parallel: the counters live in the IPC window and are never reset)
+        if (m->tp == 1) NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
         bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
         launches++;
         if (launch_tiled(m->tile_type, m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -645,7 +672,10 @@ static int record_forward(nl_model *m, int batch) {
 static int record_advance(nl_model *m, int batch) {
     StepState s{m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->gen_cap};
     // batch 1 on the tiled path: the LM-head phase of the previous forward left one (max, index) pair per CTA
-    if (batch == 1 && m->tile_ok && m->amax_valid) argmax_pairs_advance_kernel<<<1, 32, 0, m->st>>>(m->amax, m->tile_grid, s);
+    if (batch == 1 && m->tile_ok && m->amax_valid) {
+        const float2 *pairs = m->tp > 1 ? reinterpret_cast<const float2 *>(m->tp_win + m->tp_lay.tile_amax) : m->amax;
+        argmax_pairs_advance_kernel<<<1, 32, 0, m->st>>>(pairs, m->tile_grid * m->tp, s);
+    }
     else argmax_advance_kernel<<<batch, 1024, 0, m->st>>>(m->logits, m->c.vocab_size, s);
     NL_CUDA(cudaGetLastError());
     return NL_OK;
@@ -1373,6 +1403,8 @@ int nl_tp_import_handles(nl_model *m, const void *handles64_by_rank, int32_t n_r
         m->tp_peers.win[r] = (uint8_t *)p;
     }
     m->tp_ready = true;
+    rc = build_tiled(m);   // the shards as tiles, exchange inside the persistent kernel (falls back to the per-matrix chain when not eligible)
+    if (rc) { m->tp_ready = false; return rc; }
     rc = build_graphs(m, 1);
     if (rc) { m->tp_ready = false; return rc; }
     return NL_OK;

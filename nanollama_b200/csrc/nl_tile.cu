@@ -109,6 +109,23 @@ __device__ __forceinline__ void wait_relaxed(const unsigned int *bar, int p, uns
     } while (v < G);
 }
 
+// Grid barrier of phase p.  Single GPU: counters zeroed before every launch, target = grid.  Tensor parallel: counters live in the
+// IPC window, are never reset (target = epoch x grid x ranks-that-arrive) and a phase whose outputs go to the peers (`cross`) is
+// arrived at on EVERY rank's counter after a system-scope fence, so passing it means every rank's partials have landed here.
+__device__ __forceinline__ void tl_arrive(const TileArgs &A, int p, bool cross, bool ll) {
+    if (A.tp <= 1) { arrive_relaxed(A.bar, p, ll); return; }
+    if (!cross) { phase_arrive(A.bar, p); return; }
+    __threadfence_system();
+    for (int r = 0; r < A.tp; r++)
+        asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned int *>(A.peers.win[r] + A.bar_off) + p) : "memory");
+}
+__device__ __forceinline__ void tl_wait(const TileArgs &A, int p, bool cross, unsigned int G, unsigned int epoch, bool ll) {
+    if (A.tp <= 1) { wait_relaxed(A.bar, p, G, ll); return; }
+    const unsigned int target = epoch * G * (cross ? (unsigned)A.tp : 1u);
+    if (cross) { while ((int)(ld_acquire_sys(A.bar + p) - target) < 0) {} }
+    else { while ((int)(ld_acquire(A.bar + p) - target) < 0) { __nanosleep(20); } }
+}
+
 // shared-memory accessors on raw 32-bit shared addresses (all address arithmetic stays in 32-bit integer registers, computed once)
 __device__ __forceinline__ uint4 lds128(uint32_t a) {
     uint4 v;
@@ -458,7 +475,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     const int G = gridDim.x;
-    const unsigned int flag_base = (A.epoch ? __ldg(A.epoch) : 0u) * (unsigned)(A.n_phases + 1);
+    const unsigned int epoch = A.epoch ? __ldg(A.epoch) : 0u;
+    const unsigned int flag_base = epoch * (unsigned)(A.n_phases + 1);
     const bool ll = A.ll != 0;
     if (tid == 0) {
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
@@ -508,6 +526,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *resid_src = ldg_ptr(&P->resid);
             const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);
             const unsigned int oflag = flag_base + (unsigned)p + 1u;
+            const int exch_out = __ldg(&P->exch_out), par = __ldg(&P->par), cross = __ldg(&P->cross);
+            const bool to_peers_logits = A.tp > 1 && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
             const int cols_p = __ldg(&P->cols);
             int u0, u1;
@@ -525,7 +545,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 // slot of a phase: only a consumed slot proves that this CTA is past the grid barrier that orders the residual's writers)
                 float resid = 0.f;
                 int q_done = -1;
-                if (epi == TEPI_RESID && c0 > 0) {
+                if (epi == TEPI_RESID && c0 > 0 && !exch_out) {
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
                     if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r); }
                 }
@@ -566,9 +586,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                             const int r = rg * 16 + row;
                             if (half == 0 && r < rows) {
                                 if (bias) v += __ldg(bias + r);
-                                if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
-                                if (out_ll) st_ll(out, r, v, oflag); else out[r] = v;
-                                if (v > best || (v == best && r < best_i)) { best = v; best_i = r; }   // first maximum, go/main.go:400-408
+                                if (exch_out) {          // this rank's partial of a row-split product -> slot `rank` on every rank (NVLink stores)
+                                    for (int rr = 0; rr < A.tp; rr++)
+                                        reinterpret_cast<float *>(A.peers.win[rr] + A.ar_off)[((size_t)par * A.tp + A.rank) * A.dim + r] = v;
+                                } else if (to_peers_logits) {   // vocab-split LM head: my rows of the full logits vector on every rank
+                                    for (int rr = 0; rr < A.tp; rr++) reinterpret_cast<float *>(A.peers.win[rr] + A.lg_off)[(size_t)A.rank * A.lvocab + r] = v;
+                                } else {
+                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                    if (out_ll) st_ll(out, r, v, oflag); else out[r] = v;
+                                }
+                                const int gr = A.tp > 1 ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
+                                if (v > best || (v == best && gr < best_i)) { best = v; best_i = gr; }   // first maximum, go/main.go:400-408
                             }
                         }
                     }
@@ -583,10 +611,15 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     const int oi = __shfl_xor_sync(0xffffffffu, best_i, o);
                     if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
                 }
-                if (lane == 0) A.amax[blockIdx.x] = make_float2(best, __int_as_float(best_i));
+                if (lane == 0) {
+                    if (A.tp > 1) {
+                        for (int rr = 0; rr < A.tp; rr++)
+                            reinterpret_cast<float2 *>(A.peers.win[rr] + A.amax_off)[A.rank * gridDim.x + blockIdx.x] = make_float2(best, __int_as_float(best_i));
+                    } else A.amax[blockIdx.x] = make_float2(best, __int_as_float(best_i));
+                }
             }
             __syncwarp();
-            if (lane == 0) { TL_TRACE(p, 4); arrive_relaxed(A.bar, p, ll); TL_TRACE(p, 6); }   // flagged outputs: no fence
+            if (lane == 0) { TL_TRACE(p, 4); tl_arrive(A, p, cross != 0, ll); TL_TRACE(p, 6); }
             __syncwarp();
         }
         return;
@@ -613,7 +646,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         const int kind = P.kind, layer = P.layer, nbg = P.nbg, cols = P.cols;
         const unsigned int magic = P.nbg_magic;
         const float *px = P.x, *pnw = P.norm_w;
-        const int in_ll = P.in_ll;
+        const int in_ll = P.in_ll, in_exch = P.in_exch, wait_cross = P.wait_cross, xpar = P.par;
+        const float *xprev = P.prev;
+        float *xnext = P.next;
         int u0, u1;
         band_of(P.n_rg / P.unit_rg, blockIdx.x, G, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
@@ -631,7 +666,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                            min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
                 pre = true;
             }
-            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G, ll); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch, ll); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
             for (int item = blockIdx.x; item < n_items; item += G) {
                 attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u, ll,
@@ -640,7 +675,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             }
             if (!ll) __threadfence();
             tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores (flagged ones carry their own flags; the KV rows are for later tokens)
-            if (tid == 0) { TL_TRACE(p, 3); arrive_relaxed(A.bar, p, ll); TL_TRACE(p, 4); }
+            if (tid == 0) { TL_TRACE(p, 3); tl_arrive(A, p, false, ll); TL_TRACE(p, 4); }
             continue;
         }
 
@@ -659,7 +694,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             }
         }
         if (p > 0) {
-            if (tid == 0) { TL_TRACE(p, 0); wait_relaxed(A.bar, p - 1, (unsigned)G, ll); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch, ll); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
@@ -676,7 +711,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 #pragma unroll
             for (int i = 0; i < 8; i++) y[i] = 0.f;
             if (q < nitem) {
-                if (in_ll) {   // 8 flagged elements = 64 bytes; look again until all eight carry this phase's input flag
+                if (in_exch) {   // residual + every rank's partial of the row-split product, in rank order (the all-reduce)
+                    const float4 a = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q + 1);
+                    y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+                    const float *parts = reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) + (size_t)xpar * A.tp * A.dim;
+                    for (int rr = 0; rr < A.tp; rr++) {
+                        const float4 c = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * A.dim) + 2 * q), d = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * A.dim) + 2 * q + 1);
+                        y[0] += c.x; y[1] += c.y; y[2] += c.z; y[3] += c.w; y[4] += d.x; y[5] += d.y; y[6] += d.z; y[7] += d.w;
+                    }
+                    if (u0 == 0) {   // (the CTA that holds the matrix's first unit) the new residual, read back at the next exchange
+                        reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
+                        reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
+                    }
+                } else if (in_ll) {   // 8 flagged elements = 64 bytes; look again until all eight carry this phase's input flag
                     const uint4 *src = reinterpret_cast<const uint4 *>(px) + 4 * q;
                     const unsigned int want = flag_base + (unsigned)p;
                     uint4 a0, a1, a2, a3;
@@ -759,10 +806,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (tid == 0) TL_TRACE(p, 2);
 
         // ---- stream the band ----
+        if (in_exch && u0 == 0) __threadfence();
         it = stream_band<TYPE>(band, nbg, magic, it, warp, lane, smem_u32(ring), smem_u32(xfrag), smem_u32(corr), smem_u32(&sh.full_bar[0]),
                          smem_u32(&sh.empty_bar[0]), smem_u32(&sh.red[0][warp][0][lane >> 2]));
         if (tid == 0) TL_TRACE(p, 3);
     }
+    // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
+    if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch, ll);
 }
 
 template <int TYPE>

@@ -31,6 +31,7 @@
 #include "nl_common.cuh"
 #include "nl_stream.cuh"  // PTX wrappers
 #include "nl_mega.cuh"    // MegaAttn, attn_item, grid-barrier helpers
+#include "nl_tp.cuh"      // TpPeers: peer windows of a tensor-parallel group
 
 namespace nl {
 
@@ -76,6 +77,16 @@ struct TilePhase {
     float *out;               // output vector (plain, or flagged pairs when out_ll)
     const float *resid;       // TEPI_RESID: the vector the product is added to (plain, or flagged pairs when resid_ll)
     int in_ll, out_ll, resid_ll;
+    // ---- tensor parallel (TileArgs::tp > 1) ----
+    int exch_out;             // row-split matrix (O / down): the product is this rank's PARTIAL; it is stored into slot `rank` of
+                              // parity `par` of every peer's exchange area instead of being added to the residual
+    int in_exch;              // input = prev + sum over ranks of the exchange area's parity `par` (fixed rank order: identical everywhere);
+                              // CTA 0 also stores it to `next`, the residual of the following exchange
+    int par;
+    int cross;                // this phase's outputs travel to peers: its barrier counts every CTA of every rank
+    int wait_cross;           // `cross` of the previous phase (whose barrier this phase waits on)
+    const float *prev;
+    float *next;
 };
 
 struct TileArgs {
@@ -83,6 +94,10 @@ struct TileArgs {
     int n_phases;
     unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
     const unsigned int *epoch;  // launch counter behind the flags of flagged {value, flag} vectors (attention partials; activations when ll)
+    // tensor parallel: one process per GPU, peers' windows mapped through CUDA IPC (nl_tp.cuh); offsets are the same in every window
+    int tp, rank, dim, lvocab;
+    TpPeers peers;
+    unsigned long long ar_off, bar_off, lg_off, amax_off;   // exchange area [2][tp][dim] f32 | barrier counters | full logits | [tp][grid] argmax pairs
     float2 *amax;             // optional [grid]: per CTA (maximum, index as int bits) of the last phase's outputs (device-side greedy)
     int ll;                   // 1: activation vectors are flagged pairs and the grid barriers carry no fence
     MegaAttn at;

@@ -18,6 +18,8 @@ struct TpLayout {
     size_t ar_flag;   // uint32 [2][TP_MAX]   (padded to 128 B per parity)
     size_t lg_data;   // float [vocab]          full logits, every rank writes its shard into every window
     size_t lg_flag;   // uint32 [TP_MAX]
+    size_t tile_bar;  // uint32 [1024]          phase-barrier counters of the persistent tiled kernel (never reset)
+    size_t tile_amax; // float2 [TP_MAX][256]   per-CTA argmax pairs of every rank's LM-head shard
     size_t total;
 };
 inline TpLayout tp_layout(int tp, int dim, int vocab) {
@@ -26,7 +28,9 @@ inline TpLayout tp_layout(int tp, int dim, int vocab) {
     L.ar_data = o; o += (size_t)2 * tp * dim * 4; o = (o + 255) / 256 * 256;
     L.ar_flag = o; o += 2 * 128; o = (o + 255) / 256 * 256;
     L.lg_data = o; o += (size_t)vocab * 4; o = (o + 255) / 256 * 256;
-    L.lg_flag = o; o += 128;
+    L.lg_flag = o; o += 128; o = (o + 255) / 256 * 256;
+    L.tile_bar = o; o += 1024 * 4;
+    L.tile_amax = o; o += (size_t)TP_MAX * 256 * 8;
     L.total = (o + 255) / 256 * 256;
     return L;
 }
