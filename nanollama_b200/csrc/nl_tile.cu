@@ -562,10 +562,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     // warp w dropped this row group's sums into entry 0, unless its first tile still belonged to the previous group
                     // (then: entry 1); independent loads first, one fixed summation tree after (deterministic)
                     float pv[TL_CW / 2];
+                    const float *rb = &sh.red[slot][0][0][row];   // + 32 floats per warp, + 16 for entry 1
+                    if (a == 0 && b == TS) {   // the common case: the whole slot is one row group, every warp's entry 0
 #pragma unroll
-                    for (int i = 0; i < TL_CW / 2; i++) {
-                        const int w = wa + half + 2 * i;
-                        pv[i] = (w <= wb) ? sh.red[slot][w][(w == wa && TPW * w < a) ? 1 : 0][row] : 0.f;
+                        for (int i = 0; i < TL_CW / 2; i++) pv[i] = rb[(half + 2 * i) * 32];
+                    } else {
+#pragma unroll
+                        for (int i = 0; i < TL_CW / 2; i++) {
+                            const int w = wa + half + 2 * i;
+                            pv[i] = (w <= wb) ? rb[w * 32 + ((w == wa && TPW * w < a) ? 16 : 0)] : 0.f;
+                        }
                     }
                     float s = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
                     s += __shfl_xor_sync(0xffffffffu, s, 16);

@@ -1,3 +1,4 @@
-N=$(nvidia-smi -L | wc -l)
-timeout 900 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29511 tests/tp_worker.py > gpurun_out/tp$N.log 2>&1; echo "tp$N parity rc=$?"; grep "\[tp\]\|TP_PARITY\|Error\|error" gpurun_out/tp$N.log | tail -12
-timeout 600 python -m torch.distributed.run --nnodes=1 --nproc-per-node $N --master-addr 127.0.0.1 --master-port 29512 bench.py --gpus $N --steps 3 --warmup 3 > gpurun_out/bench_tp$N.json 2> gpurun_out/bench_tp$N.err; echo "bench tp$N rc=$?"; tail -1 gpurun_out/bench_tp$N.json | cut -c1-200
+timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "wide_tier or forward_logits or greedy_stream or tier_greedy" > gpurun_out/pytest_quick.log 2>&1; echo "quick rc=$?"; tail -3 gpurun_out/pytest_quick.log
+timeout 120 python tools/gemv_bench.py --rows 96000 --cols 4096 2>&1 | tail -1
+timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'])"
+timeout 300 python tools/decode_ctx_bench.py 2>&1 | tail -1
