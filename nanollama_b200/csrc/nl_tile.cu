@@ -147,6 +147,18 @@ __device__ __forceinline__ void mbar_wait_u(uint32_t bar, uint32_t parity) {
         "bra WAIT_LOOP;\n\t"
         "WAIT_DONE:\n\t}" ::"r"(bar), "r"(parity) : "memory");
 }
+// wait with a suspend-time hint: the hardware parks the warp until the phase completes (or the hint elapses) instead of letting it
+// re-issue try_wait back to back.  The copy and finishing warps wait most of the time; spinning, they executed 7 % of all the kernel's
+// instructions (ncu source counters) on the two SM sub-partitions they share with math warps.
+__device__ __forceinline__ void mbar_wait_parked(uint64_t *bar, uint32_t parity) {
+    asm volatile(
+        "{\n\t.reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1, %2;\n\t"
+        "@p bra WAIT_DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "WAIT_DONE:\n\t}" ::"r"(smem_u32(bar)), "r"(parity), "r"(20000u) : "memory");
+}
 __device__ __forceinline__ void mbar_arrive_u(uint32_t bar) { asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(bar) : "memory"); }
 
 // B fragments of one block group: only the lane that owns (block column, hi|lo) of B holds data, every other lane keeps zeros
@@ -500,10 +512,10 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const uint8_t *src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TILE;
             for (int c0 = 0; c0 < band; c0 += TS, it++) {
                 const int slot = it % TL_SLOTS;
-                if (it >= TL_SLOTS) mbar_wait(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
+                if (it >= TL_SLOTS) mbar_wait_parked(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
                 // at most `inflight` copies on the wire: bytes requested but not yet landed are queue in front of every other
                 // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
-                if (it >= A.inflight) mbar_wait(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
+                if (it >= A.inflight) mbar_wait_parked(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
                 const uint32_t bytes = (uint32_t)min(TS, band - c0) * TILE;
                 mbar_expect_tx(&sh.full_bar[slot], bytes);
                 bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)c0 * TILE, bytes, &sh.full_bar[slot], policy);
@@ -549,7 +561,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
                     if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r); }
                 }
-                mbar_wait(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
+                mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
                 if (lane == 0 && c1 == band) TL_TRACE(p, 5);   // last slot consumed by every math warp
                 if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607: inv = 1 / sqrt(ss / n + eps) from the float64 sum of squares
                     double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);   // fixed butterfly order: deterministic
