@@ -86,25 +86,30 @@ class ClockSampler:
 
 
 def cpu_reference_toks(tier: str, typ: int, n_tokens: int, pos0: int):
-    """CPU restatement of the Go engine on the host cores, bounded sample: the tier truncated to 2 and to 4 layers (full
-    width, full vocab), n_tokens decode steps each; per-layer and head costs extrapolated linearly to the full depth."""
+    """CPU restatement of the Go engine on the host cores, bounded sample: the tier truncated to 2 and to 6 layers (full
+    width, full vocab), n_tokens decode steps each (median per-token time); per-layer and head costs extrapolated linearly to
+    the full depth."""
     from nanollama_b200 import tiers as T
     from oracle import oracle as O
     full_layers = T.TIERS[tier][0]
+    lo, hi = 2, min(6, full_layers)
     times = {}
-    for nl in (2, 4):
+    for nl in (lo, hi):
         gf = T.SyntheticGGUF(tier, typ, seed=0, seq_len=PROMPT_LEN + 64, layers=nl)
         o = O.OracleModel(gf)
         o.forward(1, 0)  # warm (page in weights)
-        t0 = time.perf_counter()
+        per_tok = []
         for i in range(n_tokens):
+            t0 = time.perf_counter()
             o.forward(3 + i, pos0 + i if pos0 + i < PROMPT_LEN + 64 else 1 + i)
-        times[nl] = (time.perf_counter() - t0) / n_tokens
+            per_tok.append(time.perf_counter() - t0)
+        times[nl] = float(np.median(per_tok))
         o.close()
-    per_layer = max((times[4] - times[2]) / 2, 1e-9)
-    head = max(times[2] - 2 * per_layer, 0.0)
+    per_layer = max((times[hi] - times[lo]) / max(hi - lo, 1), 1e-9) if hi > lo else times[lo] / lo
+    head = max(times[lo] - lo * per_layer, 0.0)
     t_full = full_layers * per_layer + head
-    return 1.0 / t_full, O.get_workers(), f"{tier} truncated to 2 and 4 layers x {n_tokens} tokens, extrapolated to {full_layers} layers + LM head"
+    return 1.0 / t_full, O.get_workers(), (f"{tier} truncated to {lo} and {hi} layers x {n_tokens} tokens (median per-token time), "
+                                           f"extrapolated to {full_layers} layers + LM head")
 
 
 def main():
@@ -117,7 +122,7 @@ def main():
     ap.add_argument("--dtype", default="q4_0", choices=["q4_0", "q8_0", "f16"])
     ap.add_argument("--tokens-per-step", type=int, default=256)
     ap.add_argument("--no-cpu-baseline", action="store_true")
-    ap.add_argument("--cpu-tokens", type=int, default=2)
+    ap.add_argument("--cpu-tokens", type=int, default=8)
     args = ap.parse_args()
 
     rank = int(os.environ.get("RANK", "0"))

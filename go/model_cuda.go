@@ -172,6 +172,9 @@ func (m *LlamaModel) GenerateGreedyCUDA(prompt []int, maxTokens, eosID int) ([]i
 }
 
 // Close releases the device memory (there is no counterpart in the reference: its weights are Go slices).
+// DecodePath names the kernel family that runs a batch-1 Forward of this model ("decode_tiled_kernel", ...): for the banner / logs.
+func (m *LlamaModel) DecodePath() string { return C.GoString(C.nl_decode_path(m.cuda.h)) }
+
 func (m *LlamaModel) Close() {
 	if m.cuda != nil && m.cuda.h != nil {
 		C.nl_destroy(m.cuda.h)

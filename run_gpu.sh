@@ -1,3 +1,6 @@
-timeout 900 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 600 -k "wide_tier or forward_logits or greedy_stream" > gpurun_out/pytest_quick.log 2>&1; echo "quick rc=$?"; tail -3 gpurun_out/pytest_quick.log
-timeout 120 python tools/gemv_bench.py --rows 96000 --cols 4096 2>&1 | tail -1
-timeout 300 python bench.py --steps 3 --warmup 3 --no-cpu-baseline 2>&1 | tail -1 | python -c "import sys,json; d=json.loads(sys.stdin.read()); print(d['value'], d['roofline']['frac'])"
+timeout 1500 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_big.json 2> gpurun_out/bench_big.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/bench_big.json
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | tail -1 | cut -c1-200
+timeout 900 ncu --set full --clock-control none --import-source on -k regex:decode_tiled -s 20 -c 1 -o gpurun_out/prof_tiled python bench.py --steps 1 --warmup 1 --tokens-per-step 32 --no-cpu-baseline > gpurun_out/ncu_tiled.log 2>&1; echo "ncu full rc=$?"
+timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode_tiled|embed_kernel|argmax|bump_epoch|feed_prompt" -c 300 --csv --log-file gpurun_out/launches_big_decode.csv python bench.py --steps 1 --warmup 1 --tokens-per-step 32 --no-cpu-baseline > gpurun_out/ncu_big.log 2>&1; echo "ncu list rc=$?"
