@@ -272,6 +272,7 @@ struct nl_model {
     std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
     // flagged {value, flag} activation vectors of the tiled path: residual stream, q | k | v, attention output, SwiGLU output
     uint2 *x_ll = nullptr, *qkv_ll = nullptr, *ao_ll = nullptr, *hb_ll = nullptr;
+    float *arena = nullptr; size_t arena_bytes = 0;   // polled single-use activation vectors of the tiled path (nl_tile.cu)
     unsigned int *d_epoch = nullptr;    // launch counter behind the flags
     float2 *amax = nullptr; bool amax_valid = false;   // per-CTA argmax pairs of the LM-head phase
     float *qkv_bias = nullptr;
@@ -476,11 +477,17 @@ static int build_tiled(nl_model *m) {
     std::vector<TilePhase> ph;
     TilePhase P;
     int rc;
-    // default: plain fp32 vectors (the pair buffers are then used as plain arrays) behind release / acquire barriers.
-    // NL_TILE_LL=1: flagged {value, flag} vectors with fence-free barriers -- measured slower on B200 (the arrival overtakes the
-    // data, the first look fails and costs a second L2 round trip; 2x the bytes per phase input), kept for experiments
-    const int LL = (!tpar && getenv("NL_TILE_LL") && atoi(getenv("NL_TILE_LL")) == 1) ? 1 : 0;
-    void *xres = LL ? (void *)m->x_ll : (void *)m->x;
+    // Single GPU: polled single-use activation vectors, no grid barrier (nl_tile.cu, "polled activations"); per layer
+    // q|k|v, attention output, post-attention residual, SwiGLU output, layer output live in one arena that record_forward fills with
+    // the sentinel before every launch.  NL_TILE_POLL=0 (and tensor parallel): shared vectors behind release / acquire grid barriers.
+    const int LL = (!tpar && !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0)) ? 1 : 0;
+    const size_t per_layer = (size_t)nqkv + qdim + dim + ffn + dim;
+    if (LL) {
+        m->arena_bytes = (size_t)c.n_layers * per_layer * 4;
+        NL_CUDA(cudaMalloc(&m->arena, m->arena_bytes));
+        NL_CUDA(cudaMemset(m->arena, 0xFF, m->arena_bytes));
+    }
+    void *xres = (void *)m->x;
     // tensor parallel: exchange e (o-projection of layer l: e = 2l, down-projection: e = 2l + 1) uses parity e & 1 of the exchange area;
     // its consumer adds the ranks' partials to the residual before it (the embedding for e = 0, else xres2[(e - 1) & 1]) and leaves
     // the sum in xres2[e & 1]
@@ -500,25 +507,31 @@ static int build_tiled(nl_model *m) {
         m->tile_bufs.push_back(t_gu);
         if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_dn);
-        // layer 0 reads the embedding kernel's plain x; from then on the residual stream lives in x_ll
-        const void *x_in = (l == 0 || !LL) ? (const void *)m->x : (const void *)m->x_ll;
-        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, LL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, m->qkv_ll, LL);
+        // this layer's vectors: shared buffers, or (polled) its own slice of the arena; layer 0 reads the embedding kernel's plain x
+        float *a_l = LL ? m->arena + (size_t)l * per_layer : nullptr;
+        void *qkv_l = LL ? (void *)a_l : (void *)m->qkv_ll, *ao_l = LL ? (void *)(a_l + nqkv) : (void *)m->ao_ll;
+        void *hb_l = LL ? (void *)(a_l + nqkv + qdim + dim) : (void *)m->hb_ll;
+        const void *x_in = (l == 0 || !LL) ? (const void *)m->x : (const void *)(a_l - dim);   // the layer before's output
+        if (LL) xres = a_l + nqkv + qdim;            // post-attention residual (output of the o-projection)
+        void *x_out = LL ? (void *)(a_l + nqkv + qdim + dim + ffn) : xres;
+        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, LL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, qkv_l, LL);
         if (tpar && l > 0) consume_exchange(P, 2 * l - 1);
         ph.push_back(P);
-        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
+        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; P.x = (const float *)qkv_l; P.out = (float *)ao_l; ph.push_back(P);
         if (tpar) {
-            tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, m->ao_ll, 0, nullptr, ly.bo, nullptr, 0);
+            tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, ao_l, 0, nullptr, ly.bo, nullptr, 0);
             P.exch_out = 1; P.par = 0; P.cross = 1;
-        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, m->ao_ll, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
+        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, ao_l, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
         ph.push_back(P);
-        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, LL, ly.ffn_norm, nullptr, m->hb_ll, LL);
+        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, LL, ly.ffn_norm, nullptr, hb_l, LL);
         if (tpar) consume_exchange(P, 2 * l);
         ph.push_back(P);
         if (tpar) {
-            tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, m->hb_ll, 0, nullptr, nullptr, nullptr, 0);
+            tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, hb_l, 0, nullptr, nullptr, nullptr, 0);
             P.exch_out = 1; P.par = 1; P.cross = 1;
-        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, m->hb_ll, LL, nullptr, nullptr, xres, LL, xres, LL);
+        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, hb_l, LL, nullptr, nullptr, x_out, LL, xres, LL);
         ph.push_back(P);
+        if (LL) xres = x_out;   // what the next layer (or the LM head) reads
     }
     {
         uint8_t *t_lm = nullptr;
@@ -544,7 +557,8 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)m->nH * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.ll = LL; a.amax = m->amax; m->amax_valid = true;
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = LL;
+    a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.amax = m->amax; m->amax_valid = true;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
@@ -581,7 +595,9 @@ static int record_forward(nl_model *m, int batch) {
     if (batch == 1 && m->tile_ok) {
         // everything after the embedding in ONE persistent tensor-core kernel (nl_tile.cuh); its grid-barrier counters start at zero
         // (tensor parallel: the counters live in the IPC window and are never reset)
-        if (m->tp == 1) NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
+        // (polled activations: no barriers; every activation vector of the token starts out as sentinels instead)
+        if (m->targs.poll) NL_CUDA(cudaMemsetAsync(m->arena, 0xFF, m->arena_bytes, st));
+        else if (m->tp == 1) NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
         bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
         launches++;
         if (launch_tiled(m->tile_type, m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
@@ -973,7 +989,7 @@ void nl_destroy(nl_model *m) {
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
-    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch, (void *)m->amax}) if (q) cudaFree(q);
+    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
     if (m->d_tphases) cudaFree(m->d_tphases);
     if (m->d_phases) cudaFree(m->d_phases);
@@ -1260,7 +1276,7 @@ static int matrix_tiles(nl_matrix *w, int n_copies) {
 }
 static int matrix_tiled_gemv(nl_matrix *w, int idx) {
     TileArgs a; memset(&a, 0, sizeof a);
-    a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar; a.inflight = tile_inflight();
+    a.phases = w->d_tph + idx; a.n_phases = 1; a.bar = w->d_tbar; a.inflight = tile_inflight(); a.att_chunk = 96;
     const int units = (int)(w->copies[0].rows / 16);
     if (launch_tiled(w->copies[0].type, a, units < w->opts.num_sms ? units : w->opts.num_sms, w->st)) return fail(NL_ERR_CUDA, "tiled gemv launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return NL_OK;

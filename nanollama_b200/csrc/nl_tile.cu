@@ -74,14 +74,10 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
 }
 #define TL_TRACE(p, k) do { if (A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
 
-// ---- flagged activations ("LL" format): every fp32 element travels as an 8-byte {value, flag} pair written by ONE store, so a reader
-// that sees the expected flag has the value too and no fence is needed between a phase's output stores and its arrival on the grid
-// barrier (the barrier only tells the readers when looking is worthwhile).  flag = epoch * (n_phases + 1) + producing phase + 1.
+// ---- flagged pairs: the un-normalised partials of a split attention item travel as 8-byte {value, flag} pairs written by ONE store, so a
+// reader that sees the expected flag has the value too (no fence, no counter).  flag = epoch * (n_phases + 1) + producing phase + 1.
 __device__ __forceinline__ void st_ll(void *base, int idx, float v, unsigned int flag) {
     asm volatile("st.volatile.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<uint2 *>(base) + idx), "r"(__float_as_uint(v)), "r"(flag) : "memory");
-}
-__device__ __forceinline__ float ld_ll_value(const void *base, int idx) {   // value of an element known to be complete
-    return __uint_as_float(__ldcg(reinterpret_cast<const unsigned int *>(base) + 2 * idx));
 }
 __device__ __forceinline__ float ld_ll_wait(const void *base, int idx, unsigned int want) {
     unsigned int v, f;
@@ -90,37 +86,51 @@ __device__ __forceinline__ float ld_ll_wait(const void *base, int idx, unsigned 
     } while (f != want);
     return __uint_as_float(v);
 }
-__device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
-    uint4 v;
-    asm volatile("ld.volatile.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
-    return v;
+// ---- polled activations (TileArgs::poll, single GPU): every activation vector of a token is written exactly ONCE (one vector per
+// layer and producer in an arena that a memset node fills with TL_SENT in front of every launch), so an element that no longer reads
+// TL_SENT IS the value: consumers poll the data itself.  No grid barrier, no fence, no flag bytes -- a phase boundary costs one
+// store -> L2 -> load trip instead of store, fence, arrive, poll, load.  Every GEMV phase needs ALL outputs of the phase before it, so
+// the data flow alone orders what the barriers ordered; single-use buffers leave no write-after-read hazard.  A computed value with
+// the sentinel's bit pattern (one particular NaN) is stored as the canonical NaN instead.
+constexpr unsigned int TL_SENT = 0xFFFFFFFFu;
+__device__ __forceinline__ void st_poll(float *base, int idx, float v) {
+    unsigned int b = __float_as_uint(v);
+    if (b == TL_SENT) b = 0x7FFFFFFFu;
+    asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(base + idx), "r"(b) : "memory");
 }
-// fence-free grid barrier: relaxed arrive, relaxed poll (correctness comes from the flags in the data)
-// (ll = false: plain vectors, release / acquire barrier)
-__device__ __forceinline__ void arrive_relaxed(unsigned int *bar, int p, bool ll) {
-    if (ll) asm volatile("red.relaxed.gpu.global.add.u32 [%0], 1;" ::"l"(bar + p) : "memory");
-    else phase_arrive(bar, p);
-}
-__device__ __forceinline__ void wait_relaxed(const unsigned int *bar, int p, unsigned int G, bool ll) {
-    if (!ll) { phase_wait(bar, p, G); return; }
+__device__ __forceinline__ float ld_poll(const float *base, int idx) {
     unsigned int v;
     do {
-        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(bar + p) : "memory");
-    } while (v < G);
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(base + idx) : "memory");
+    } while (v == TL_SENT);
+    return __uint_as_float(v);
+}
+__device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
+    uint4 v;
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%4];" : "=r"(v.x), "=r"(v.y), "=r"(v.z), "=r"(v.w) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ uint2 ld_vol_v2(const void *p) {
+    uint2 v;
+    asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ bool has_sent(const uint4 &a, const uint4 &b) {
+    return a.x == TL_SENT || a.y == TL_SENT || a.z == TL_SENT || a.w == TL_SENT || b.x == TL_SENT || b.y == TL_SENT || b.z == TL_SENT || b.w == TL_SENT;
 }
 
 // Grid barrier of phase p.  Single GPU: counters zeroed before every launch, target = grid.  Tensor parallel: counters live in the
 // IPC window, are never reset (target = epoch x grid x ranks-that-arrive) and a phase whose outputs go to the peers (`cross`) is
 // arrived at on EVERY rank's counter after a system-scope fence, so passing it means every rank's partials have landed here.
-__device__ __forceinline__ void tl_arrive(const TileArgs &A, int p, bool cross, bool ll) {
-    if (A.tp <= 1) { arrive_relaxed(A.bar, p, ll); return; }
+__device__ __forceinline__ void tl_arrive(const TileArgs &A, int p, bool cross) {
+    if (A.tp <= 1) { phase_arrive(A.bar, p); return; }
     if (!cross) { phase_arrive(A.bar, p); return; }
     __threadfence_system();
     for (int r = 0; r < A.tp; r++)
         asm volatile("red.relaxed.sys.global.add.u32 [%0], 1;" ::"l"(reinterpret_cast<unsigned int *>(A.peers.win[r] + A.bar_off) + p) : "memory");
 }
-__device__ __forceinline__ void tl_wait(const TileArgs &A, int p, bool cross, unsigned int G, unsigned int epoch, bool ll) {
-    if (A.tp <= 1) { wait_relaxed(A.bar, p, G, ll); return; }
+__device__ __forceinline__ void tl_wait(const TileArgs &A, int p, bool cross, unsigned int G, unsigned int epoch) {
+    if (A.tp <= 1) { phase_wait(A.bar, p, G); return; }
     const unsigned int target = epoch * G * (cross ? (unsigned)A.tp : 1u);
     if (cross) { while ((int)(ld_acquire_sys(A.bar + p) - target) < 0) {} }
     else { while ((int)(ld_acquire(A.bar + p) - target) < 0) { __nanosleep(20); } }
@@ -260,8 +270,9 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
     }
 }
 
-__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, const AttnItem I, int pos, bool prefetched, AttnT &S,
-                                                int tid, unsigned int want, unsigned int oflag, bool ll, unsigned long long *trace) {
+// qkv: this layer's q | k | v vector (polled element by element when `poll`), ao: its attention output
+__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float *qkv, float *ao, int layer, const AttnItem I, int pos, bool prefetched,
+                                                AttnT &S, int tid, unsigned int oflag, bool poll, unsigned long long *trace) {
     constexpr int HD = 64, HALF = 32;
     const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
     const int warp = tid >> 5, lane = tid & 31;
@@ -275,7 +286,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
         const bool isk = hh == group;
         // q | k | v are one vector [H*hd + 2*kvd] (at.q = base; at.k / at.v are element offsets from it)
         const int e0 = isk ? (int)(at.k - at.q) + kvh * HD : (kvh * group + hh) * HD;
-        const float x0 = ll ? ld_ll_wait(at.q, e0 + i, want) : __ldcg(at.q + e0 + i), x1 = ll ? ld_ll_wait(at.q, e0 + i + HALF, want) : __ldcg(at.q + e0 + i + HALF);
+        const float x0 = poll ? ld_poll(qkv, e0 + i) : __ldcg(qkv + e0 + i), x1 = poll ? ld_poll(qkv, e0 + i + HALF) : __ldcg(qkv + e0 + i + HALF);
         const float c = __ldg(at.cos_t + (size_t)pos * HALF + i), sn = __ldg(at.sin_t + (size_t)pos * HALF + i);
         float r0, r1;
         if (!at.conj) { r0 = x0 * c - x1 * sn; r1 = x0 * sn + x1 * c; }
@@ -284,7 +295,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
         dst[i] = r0; dst[i + HALF] = r1;
     } else if (tid >= TL_CONSUMERS - HD) {
         const int ev = (int)(at.v - at.q) + kvh * HD + tid - (TL_CONSUMERS - HD);
-        S.vnew[tid - (TL_CONSUMERS - HD)] = ll ? ld_ll_wait(at.q, ev, want) : __ldcg(at.q + ev);
+        S.vnew[tid - (TL_CONSUMERS - HD)] = poll ? ld_poll(qkv, ev) : __ldcg(qkv + ev);
     }
     if (tid < group) { S.m_run[tid] = -INFINITY; S.l_run[tid] = 0.f; S.corr[tid] = 0.f; }
     tl_bar<TL_CONSUMERS>();
@@ -322,7 +333,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
         tl_bar<TL_CONSUMERS>();
         {   // scores: 8 threads per position, each with 8 of the 64 dims (two conflict-free 16-byte columns), for every head of the group
             const int sub = tid & 7;
-            for (int tl = tid >> 3; tl < TA_CH; tl += TL_CONSUMERS / 8) {   // whole warps agree on tl < TA_CH
+            for (int tl = tid >> 3; tl < ((cn + 3) & ~3); tl += TL_CONSUMERS / 8) {   // a warp covers 4 consecutive positions: whole warps agree
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
                 if (tl < cn) { k0 = *reinterpret_cast<const float4 *>(&S.Ks[tl][4 * sub]); k1 = *reinterpret_cast<const float4 *>(&S.Ks[tl][32 + 4 * sub]); }
                 for (int h2 = 0; h2 < group; h2++) {
@@ -385,29 +396,37 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, int layer, c
                 st_ll(at.part_acc, (h * at.nsplit + I.sp) * HD + dd, o, pflag);
                 if (dd < 2) st_ll(at.part_ml, (h * at.nsplit + I.sp) * 2 + dd, dd == 0 ? M : den, pflag);
             } else {
-                float mo[MG_MAX_SPLIT], lo[MG_MAX_SPLIT];
-                float Mx = M;
-                for (int s = 1; s < I.nse; s++) {
-                    mo[s] = ld_ll_wait(at.part_ml, (h * at.nsplit + s) * 2, pflag);
-                    lo[s] = ld_ll_wait(at.part_ml, (h * at.nsplit + s) * 2 + 1, pflag);
-                    if (lo[s] > 0.f) Mx = fmaxf(Mx, mo[s]);
-                }
-                float w0 = den > 0.f ? expf(M - Mx) : 0.f;
-                float dsum = w0 * den, osum = w0 * o;
-                for (int s = 1; s < I.nse; s++) {
-                    const float pa = ld_ll_wait(at.part_acc, (h * at.nsplit + s) * HD + dd, pflag);
-                    if (lo[s] > 0.f) {
-                        const float wgt = expf(mo[s] - Mx);
-                        dsum = fmaf(wgt, lo[s], dsum);
-                        osum = fmaf(wgt, pa, osum);
+                // split 0 folds the others in split order (deterministic), four at a time: the looks at one group's {max, sum} pairs and
+                // partial outputs are all in flight together (one L2 round trip per group when the partials have landed), then merged
+                // with the running-softmax rule
+                const uint4 *mlp = reinterpret_cast<const uint4 *>(at.part_ml) + (size_t)h * at.nsplit;          // {M, flag, sum, flag} per split
+                const uint2 *pap = reinterpret_cast<const uint2 *>(at.part_acc) + (size_t)h * at.nsplit * HD + dd;   // + s * HD
+                for (int s0 = 1; s0 < I.nse; s0 += 4) {
+                    uint4 ml[4];
+                    uint2 pa[4];
+#pragma unroll
+                    for (int j = 0; j < 4; j++)
+                        if (s0 + j < I.nse) { ml[j] = ld_vol_v4(mlp + s0 + j); pa[j] = ld_vol_v2(pap + (size_t)(s0 + j) * HD); }
+#pragma unroll
+                    for (int j = 0; j < 4; j++) {
+                        if (s0 + j >= I.nse) break;
+                        while (ml[j].y != pflag || ml[j].w != pflag) ml[j] = ld_vol_v4(mlp + s0 + j);
+                        while (pa[j].y != pflag) pa[j] = ld_vol_v2(pap + (size_t)(s0 + j) * HD);
+                        const float ms = __uint_as_float(ml[j].x), ls = __uint_as_float(ml[j].z);
+                        if (ls > 0.f) {
+                            const float mn = fmaxf(M, ms);
+                            const float wa = den > 0.f ? expf(M - mn) : 0.f, wb = expf(ms - mn);
+                            den = fmaf(wb, ls, wa * den);
+                            o = fmaf(wb, __uint_as_float(pa[j].x), wa * o);
+                            M = mn;
+                        }
                     }
                 }
-                o = osum; den = dsum;
             }
         }
         if (I.nse == 1 || I.sp == 0) {
             const float r = o * (1.0f / den);
-            if (ll) st_ll(at.out, h * HD + dd, r, oflag); else at.out[h * HD + dd] = r;
+            if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r;
         }
     }
     tl_bar<TL_CONSUMERS>();  // S is reused by the next item of this CTA
@@ -489,7 +508,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     const int G = gridDim.x;
     const unsigned int epoch = A.epoch ? __ldg(A.epoch) : 0u;
     const unsigned int flag_base = epoch * (unsigned)(A.n_phases + 1);
-    const bool ll = A.ll != 0;
+    const bool poll = A.poll != 0;
     if (tid == 0) {
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -536,8 +555,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
             const float *resid_src = ldg_ptr(&P->resid);
-            const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);
-            const unsigned int oflag = flag_base + (unsigned)p + 1u;
+            const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);   // polled vectors (see st_poll)
             const int exch_out = __ldg(&P->exch_out), par = __ldg(&P->par), cross = __ldg(&P->cross);
             const bool to_peers_logits = A.tp > 1 && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
@@ -559,7 +577,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 int q_done = -1;
                 if (epi == TEPI_RESID && c0 > 0 && !exch_out) {
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
-                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r); }
+                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_poll(resid_src, r) : __ldcg(resid_src + r); }
                 }
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
                 if (lane == 0 && c1 == band) TL_TRACE(p, 5);   // last slot consumed by every math warp
@@ -597,7 +615,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                             else {
                                 const int r = (rg >> 1) * 16 + row;
                                 if (half == 0 && r < rows) {                                   // SiLU(gate)*up, go/model.go:604-606
-                                    if (out_ll) st_ll(out, r, silu_f(gate) * v, oflag); else out[r] = silu_f(gate) * v;
+                                    if (out_ll) st_poll(out, r, silu_f(gate) * v); else out[r] = silu_f(gate) * v;
                                 }
                             }
                         } else {
@@ -610,8 +628,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                                 } else if (to_peers_logits) {   // vocab-split LM head: my rows of the full logits vector on every rank
                                     for (int rr = 0; rr < A.tp; rr++) reinterpret_cast<float *>(A.peers.win[rr] + A.lg_off)[(size_t)A.rank * A.lvocab + r] = v;
                                 } else {
-                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_ll_value(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
-                                    if (out_ll) st_ll(out, r, v, oflag); else out[r] = v;
+                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                    if (out_ll) st_poll(out, r, v); else out[r] = v;
                                 }
                                 const int gr = A.tp > 1 ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
                                 if (v > best || (v == best && gr < best_i)) { best = v; best_i = gr; }   // first maximum, go/main.go:400-408
@@ -637,7 +655,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 }
             }
             __syncwarp();
-            if (lane == 0) { TL_TRACE(p, 4); tl_arrive(A, p, cross != 0, ll); TL_TRACE(p, 6); }
+            if (lane == 0) { TL_TRACE(p, 4); if (!poll) tl_arrive(A, p, cross != 0); TL_TRACE(p, 6); }   // polled outputs need no arrival
             __syncwarp();
         }
         return;
@@ -666,14 +684,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         const float *px = P.x, *pnw = P.norm_w;
         const int in_ll = P.in_ll, in_exch = P.in_exch, wait_cross = P.wait_cross, xpar = P.par;
         const float *xprev = P.prev;
-        float *xnext = P.next;
+        float *xnext = P.next, *pout = P.out;
         int u0, u1;
         band_of(P.n_rg / P.unit_rg, blockIdx.x, G, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
         if (kind == PH_ATTN) {
             tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
             const int pos = *A.at.pos, n = pos + 1;
-            int nse = (n + TA_CH - 1) / TA_CH;   // one prefetched pass (up to 96 positions) per split while the splits last
+            int nse = (n + A.att_chunk - 1) / A.att_chunk;   // one prefetched pass (att_chunk <= 96 positions) per split while the splits last
             nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
             const int n_items = A.at.n_kv_heads * nse;
             const int kvd = A.at.n_kv_heads * 64;
@@ -684,35 +702,44 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                            min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
                 pre = true;
             }
-            if (tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch, ll); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_TRACE(p, 0); if (!poll) tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(A.at, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p, flag_base + (unsigned)p + 1u, ll,
+                attn_item_tiled(A.at, px, pout, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p + 1u, poll,
                                 A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr);
                 pre = false;
             }
-            if (!ll) __threadfence();
-            tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores (flagged ones carry their own flags; the KV rows are for later tokens)
-            if (tid == 0) { TL_TRACE(p, 3); tl_arrive(A, p, false, ll); TL_TRACE(p, 4); }
+            if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
+            __threadfence();
+            tl_bar<TL_CONSUMERS>();   // every thread has issued its output stores
+            if (tid == 0) { TL_TRACE(p, 3); tl_arrive(A, p, false); TL_TRACE(p, 4); }
             continue;
         }
 
         // ---- prologue: phase input -> fp16 hi/lo B fragments in shared memory ----
-        const int nitem = cols >> 3, nitem_pad = nbg * 16;
         const bool normed = pnw != nullptr;
-        float wv[TL_MAX_ITEMS][8];
-        if (normed && band > 0) {   // static data: requested before we wait for the producers of x
+        const int nitem = cols >> 3, nitem_pad = nbg * 16;
+        float wv0[8];   // norm weights of my first item: static data, requested before we wait for the producers of x (items beyond
+                        // the first only exist for dim > 4096: fetched where they are used, to keep the register count down)
+        if (normed && band > 0 && tid < nitem) {
+            const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid + 1);
+            wv0[0] = a.x; wv0[1] = a.y; wv0[2] = a.z; wv0[3] = a.w; wv0[4] = b.x; wv0[5] = b.y; wv0[6] = b.z; wv0[7] = b.w;
+        }
+        // polled input: first look at all of this thread's items at once (one L2 round trip when the producers are done), issued before
+        // the block barrier so that the trip overlaps the slowest math warp's last tiles
+        uint4 xa[TL_MAX_ITEMS][2];
+        if (in_ll && band > 0) {
+            if (tid == 0) TL_TRACE(p, 0);
 #pragma unroll
             for (int r = 0; r < TL_MAX_ITEMS; r++) {
                 const int q = tid + r * TL_CONSUMERS;
-                if (q < nitem) {
-                    const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q + 1);
-                    wv[r][0] = a.x; wv[r][1] = a.y; wv[r][2] = a.z; wv[r][3] = a.w; wv[r][4] = b.x; wv[r][5] = b.y; wv[r][6] = b.z; wv[r][7] = b.w;
-                }
+                if (q < nitem) { xa[r][0] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q); xa[r][1] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q + 1); }
             }
         }
         if (p > 0) {
-            if (tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch, ll); TL_TRACE(p, 1); }
+            if (!poll && tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
+            // also: every math warp is done with the previous phase's fragments (a polled element can be complete while a slower warp of
+            // this CTA still streams the phase before), and warp 1's descriptor prefetch is ordered against its readers
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
@@ -741,23 +768,29 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                         reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
                         reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
                     }
-                } else if (in_ll) {   // 8 flagged elements = 64 bytes; look again until all eight carry this phase's input flag
-                    const uint4 *src = reinterpret_cast<const uint4 *>(px) + 4 * q;
-                    const unsigned int want = flag_base + (unsigned)p;
-                    uint4 a0, a1, a2, a3;
-                    do {
-                        a0 = ld_vol_v4(src); a1 = ld_vol_v4(src + 1); a2 = ld_vol_v4(src + 2); a3 = ld_vol_v4(src + 3);
-                    } while (a0.y != want || a0.w != want || a1.y != want || a1.w != want || a2.y != want || a2.w != want || a3.y != want || a3.w != want);
-                    y[0] = __uint_as_float(a0.x); y[1] = __uint_as_float(a0.z); y[2] = __uint_as_float(a1.x); y[3] = __uint_as_float(a1.z);
-                    y[4] = __uint_as_float(a2.x); y[5] = __uint_as_float(a2.z); y[6] = __uint_as_float(a3.x); y[7] = __uint_as_float(a3.z);
+                } else if (in_ll) {   // look again until none of my 8 elements reads as the sentinel
+                    while (has_sent(xa[r][0], xa[r][1])) {
+                        if (A.poll_ns) __nanosleep(A.poll_ns);
+                        xa[r][0] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q); xa[r][1] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q + 1);
+                    }
+                    y[0] = __uint_as_float(xa[r][0].x); y[1] = __uint_as_float(xa[r][0].y); y[2] = __uint_as_float(xa[r][0].z); y[3] = __uint_as_float(xa[r][0].w);
+                    y[4] = __uint_as_float(xa[r][1].x); y[5] = __uint_as_float(xa[r][1].y); y[6] = __uint_as_float(xa[r][1].z); y[7] = __uint_as_float(xa[r][1].w);
+                    if (tid == 0 && r == 0) TL_TRACE(p, 1);
                 } else {
                     const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
                     y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
                 }
                 if (normed) {
                     float s4 = 0.f;
+                    if (r == 0) {
 #pragma unroll
-                    for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= wv[r][i]; }
+                        for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= wv0[i]; }
+                    } else {
+                        const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q + 1);
+                        const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                        for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= w[i]; }
+                    }
                     ss += (double)s4;
                 }
             }
@@ -830,7 +863,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (tid == 0) TL_TRACE(p, 3);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
-    if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch, ll);
+    if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
 }
 
 template <int TYPE>

@@ -71,12 +71,12 @@ struct TilePhase {
     int cols;                 // input length (multiple of 32)
     int rows;                 // valid output rows (<= 16 * n_rg / unit_rg for SWIGLU, <= 16 * n_rg otherwise)
     int epi;                  // TEPI_*
-    const float *x;           // input vector [cols]: plain fp32, or {value, flag} pairs when in_ll (see nl_tile.cu)
+    const float *x;           // input vector [cols], fp32 (PH_ATTN: this layer's q | k | v vector); polled for the sentinel when in_ll
     const float *norm_w;      // non-null: input is RMSNorm(x; norm_w), go/quant.go:597-607
     const float *bias;        // optional [rows]
-    float *out;               // output vector (plain, or flagged pairs when out_ll)
-    const float *resid;       // TEPI_RESID: the vector the product is added to (plain, or flagged pairs when resid_ll)
-    int in_ll, out_ll, resid_ll;
+    float *out;               // output vector (PH_ATTN: the attention output); stored with st_poll when out_ll
+    const float *resid;       // TEPI_RESID: the vector the product is added to (polled when resid_ll)
+    int in_ll, out_ll, resid_ll;   // TileArgs::poll: the vector lives in the single-use arena (see "polled activations" in nl_tile.cu)
     // ---- tensor parallel (TileArgs::tp > 1) ----
     int exch_out;             // row-split matrix (O / down): the product is this rank's PARTIAL; it is stored into slot `rank` of
                               // parity `par` of every peer's exchange area instead of being added to the residual
@@ -93,15 +93,17 @@ struct TileArgs {
     const TilePhase *phases;
     int n_phases;
     unsigned int *bar;        // [n_phases] grid-barrier counters, zeroed before every launch
-    const unsigned int *epoch;  // launch counter behind the flags of flagged {value, flag} vectors (attention partials; activations when ll)
+    const unsigned int *epoch;  // launch counter behind the flags of the split-attention partials
     // tensor parallel: one process per GPU, peers' windows mapped through CUDA IPC (nl_tp.cuh); offsets are the same in every window
     int tp, rank, dim, lvocab;
     TpPeers peers;
     unsigned long long ar_off, bar_off, lg_off, amax_off;   // exchange area [2][tp][dim] f32 | barrier counters | full logits | [tp][grid] argmax pairs
     float2 *amax;             // optional [grid]: per CTA (maximum, index as int bits) of the last phase's outputs (device-side greedy)
-    int ll;                   // 1: activation vectors are flagged pairs and the grid barriers carry no fence
+    int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier (single GPU only)
     MegaAttn at;
     float eps;
+    int poll_ns;              // back-off between two looks at a polled phase input (0 = look again at once)
+    int att_chunk;            // attention: positions per split while the splits last (<= 96 = one pass)
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
 };
@@ -114,6 +116,11 @@ inline int tile_inflight() {
     const char *e = getenv("NL_TILE_INFLIGHT");
     int k = e ? atoi(e) : TL_SLOTS;
     return k < 1 ? 1 : (k > TL_SLOTS ? TL_SLOTS : k);
+}
+inline int tile_env_int(const char *name, int dflt, int lo, int hi) {
+    const char *e = getenv(name);
+    const int k = e ? atoi(e) : dflt;
+    return k < lo ? lo : (k > hi ? hi : k);
 }
 inline unsigned int tile_magic(int nbg) { return nbg <= 1 ? 0u : (unsigned int)(((1ull << 32) + (unsigned)nbg - 1) / (unsigned)nbg); }
 
