@@ -9,7 +9,8 @@ import ctypes as C
 import os
 
 PKG = os.path.dirname(os.path.abspath(__file__))
-LIB_PATH = os.path.join(PKG, "libnanollama_cuda.so")
+# NL_LIB: a differently built copy of the same library (tools/build_variants.py), for A/B runs of build-time variants
+LIB_PATH = os.environ.get("NL_LIB") or os.path.join(PKG, "libnanollama_cuda.so")
 
 NL_OK, NL_ERR_INVALID, NL_ERR_CUDA, NL_ERR_UNSUPPORTED, NL_ERR_STATE, NL_ERR_OOM = 0, -1, -2, -3, -4, -5
 

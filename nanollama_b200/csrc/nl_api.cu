@@ -14,6 +14,7 @@
 #include "nl_stream.cuh"
 #include "nl_mega.cuh"
 #include "nl_tile.cuh"
+#include <string>
 #include "nl_tp.cuh"
 #include "nl_gemm.cuh"
 #include "nl_prefill.cuh"
@@ -265,7 +266,7 @@ struct nl_model {
     bool mega_ok = false;
     MegaPhase *d_phases = nullptr; unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;
     MegaArgs margs; int mega_grid = 0; size_t mega_smem = 0; int mega_type = -1;
-    unsigned long long *d_trace = nullptr;
+    unsigned long long *d_trace = nullptr, *d_trace2 = nullptr;
     int mega_reps = 1;
     // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
     bool tile_ok = false; int tile_type = NL_Q4_0;
@@ -574,6 +575,9 @@ static int build_tiled(nl_model *m) {
         NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
         NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
         a.trace = m->d_trace;
+        NL_CUDA(cudaMalloc(&m->d_trace2, (size_t)G * ph.size() * 16 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMemset(m->d_trace2, 0, (size_t)G * ph.size() * 16 * sizeof(unsigned long long)));
+        a.trace2 = m->d_trace2;
     }
     m->tile_grid = G; m->tile_type = wtype;
     m->tile_ok = true;
@@ -987,6 +991,7 @@ void nl_destroy(nl_model *m) {
         if (m->d_lg_epoch) cudaFree(m->d_lg_epoch);
     }
     if (m->d_trace) cudaFree(m->d_trace);
+    if (m->d_trace2) cudaFree(m->d_trace2);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
     for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
@@ -1200,6 +1205,13 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
         NL_CUDA(cudaMemcpy(h.data(), m->d_trace, n * 8, cudaMemcpyDeviceToHost));
         FILE *f = fopen(getenv("NL_TRACE"), "wb");
         if (f) { int hdr[2] = {tg, tp_}; fwrite(hdr, 4, 2, f); fwrite(h.data(), 8, n, f); fclose(f); }
+        if (m->d_trace2 && m->tile_ok) {   // clock64 sub-stamps -> <NL_TRACE>.ck
+            std::vector<unsigned long long> h2(n * 2);
+            NL_CUDA(cudaMemcpy(h2.data(), m->d_trace2, n * 16, cudaMemcpyDeviceToHost));
+            std::string p2 = std::string(getenv("NL_TRACE")) + ".ck";
+            FILE *f2 = fopen(p2.c_str(), "wb");
+            if (f2) { int hdr2[2] = {tg, tp_}; fwrite(hdr2, 4, 2, f2); fwrite(h2.data(), 8, n * 2, f2); fclose(f2); }
+        }
     }
     return NL_OK;
 }

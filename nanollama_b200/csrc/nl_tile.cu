@@ -73,6 +73,30 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
     return reinterpret_cast<T *>(__ldg(reinterpret_cast<const unsigned long long *>(p)));
 }
 #define TL_TRACE(p, k) do { if (A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
+// fine-grained forensics (compile with -DNL_TL_FINE_TRACE=1; off by default: the stamps cost registers in the phase loop): SM cycle
+// counter (clock64) stamps, 16 per (CTA, phase); see tools/trace_fine.py for the slot meanings
+#ifndef NL_TL_FINE_TRACE
+#define NL_TL_FINE_TRACE 0
+#endif
+#if NL_TL_FINE_TRACE
+#define TL_CK(p, k) do { if (A.trace2) A.trace2[((size_t)blockIdx.x * A.n_phases + (p)) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+#define CK_AT(k) do { if (ck) ck[k] = (unsigned long long)clock64(); } while (0)
+#else
+#define TL_CK(p, k) do { } while (0)
+#define CK_AT(k) do { } while (0)
+#endif
+// build-time variants of the register allocation around the streaming loop (tools/build_variants.py A/Bs them)
+#ifndef NL_TL_FRAGS_INLINE
+#define NL_TL_FRAGS_INLINE 0
+#endif
+#if NL_TL_FRAGS_INLINE
+#define TL_FRAGS_CALL __forceinline__
+#else
+#define TL_FRAGS_CALL __noinline__
+#endif
+#ifndef NL_TL_XB_SINGLE
+#define NL_TL_XB_SINGLE 1
+#endif
 
 // ---- flagged pairs: the un-normalised partials of a split attention item travel as 8-byte {value, flag} pairs written by ONE store, so a
 // reader that sees the expected flag has the value too (no fence, no counter).  flag = epoch * (n_phases + 1) + producing phase + 1.
@@ -114,6 +138,14 @@ __device__ __forceinline__ uint2 ld_vol_v2(const void *p) {
     uint2 v;
     asm volatile("ld.relaxed.gpu.global.v2.u32 {%0,%1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(p) : "memory");
     return v;
+}
+// 8 consecutive floats of a polled vector as raw words (two 16-byte loads)
+__device__ __forceinline__ void ld_item(const float *base, int q, unsigned int (&w)[8]) {
+    asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%8];\n\tld.relaxed.gpu.global.v4.u32 {%4,%5,%6,%7}, [%8+16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(base + 8 * (size_t)q) : "memory");
+}
+__device__ __forceinline__ bool item_has_sent(const unsigned int (&w)[8]) {
+    return max(max(max(w[0], w[1]), max(w[2], w[3])), max(max(w[4], w[5]), max(w[6], w[7]))) == TL_SENT;   // the sentinel is the largest word
 }
 __device__ __forceinline__ bool has_sent(const uint4 &a, const uint4 &b) {
     return a.x == TL_SENT || a.y == TL_SENT || a.z == TL_SENT || a.w == TL_SENT || b.x == TL_SENT || b.y == TL_SENT || b.z == TL_SENT || b.w == TL_SENT;
@@ -272,7 +304,8 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
 
 // qkv: this layer's q | k | v vector (polled element by element when `poll`), ao: its attention output
 __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float *qkv, float *ao, int layer, const AttnItem I, int pos, bool prefetched,
-                                                AttnT &S, int tid, unsigned int oflag, bool poll, unsigned long long *trace) {
+                                                AttnT &S, int tid, unsigned int oflag, bool poll, unsigned long long *trace, unsigned long long *ck) {
+    if (tid != 0) ck = nullptr;
     constexpr int HD = 64, HALF = 32;
     const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
     const int warp = tid >> 5, lane = tid & 31;
@@ -298,6 +331,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         S.vnew[tid - (TL_CONSUMERS - HD)] = poll ? ld_poll(qkv, ev) : __ldcg(qkv + ev);
     }
     if (tid < group) { S.m_run[tid] = -INFINITY; S.l_run[tid] = 0.f; S.corr[tid] = 0.f; }
+    CK_AT(2);
     tl_bar<TL_CONSUMERS>();
     if (tid == 0 && trace) trace[5] = gtime();   // q / k / v in shared memory
     if (at.qk_norm) {
@@ -311,6 +345,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         }
         tl_bar<TL_CONSUMERS>();
     }
+    CK_AT(3);
     if (owner && tid < HD) {   // KV write, go/model.go:552-554
         kc[(size_t)pos * kvd + kvh * HD + tid] = S.knew[tid];
         vc[(size_t)pos * kvd + kvh * HD + tid] = S.vnew[tid];
@@ -331,6 +366,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         }
         cp_async_wait_all();
         tl_bar<TL_CONSUMERS>();
+        if (pass == 0) CK_AT(4);
         {   // scores: 8 threads per position, each with 8 of the 64 dims (two conflict-free 16-byte columns), for every head of the group
             const int sub = tid & 7;
             for (int tl = tid >> 3; tl < ((cn + 3) & ~3); tl += TL_CONSUMERS / 8) {   // a warp covers 4 consecutive positions: whole warps agree
@@ -347,6 +383,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
             }
         }
         tl_bar<TL_CONSUMERS>();
+        if (pass == 0) CK_AT(5);
         if (warp < group) {  // running softmax statistics of head `warp` (flash-decoding form of go/quant.go:610-626)
             const float s0 = lane < cn ? S.p[warp][lane] : -INFINITY, s1 = lane + 32 < cn ? S.p[warp][lane + 32] : -INFINITY;
             const float s2 = lane + 64 < cn ? S.p[warp][lane + 64] : -INFINITY;
@@ -365,6 +402,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
             }
         }
         tl_bar<TL_CONSUMERS>();
+        if (pass == 0) CK_AT(6);
         if (part < nparts) {   // PV: thread = (part of the positions, head, 4 dims)
             const float cr = S.corr[hh];
             float4 a = make_float4(acc4.x * cr, acc4.y * cr, acc4.z * cr, acc4.w * cr);
@@ -376,11 +414,13 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
             acc4 = a;
         }
         tl_bar<TL_CONSUMERS>();
+        if (pass == 0) CK_AT(7);
         if (tid == 0 && trace && pass == 0) trace[2] = gtime();   // first pass done
     }
     float *pvs = &S.Ks[0][0];   // every pass is over (the loop ends on a barrier): the K rows become the PV partials
     *reinterpret_cast<float4 *>(&pvs[tid * 4]) = acc4;
     tl_bar<TL_CONSUMERS>();
+    CK_AT(8);
     if (tid == 0 && trace) trace[6] = gtime();   // own positions done
     if (tid < gthreads) {
         const int hh = tid >> 6, dd = tid & 63;            // (shadows the PV mapping)
@@ -429,22 +469,42 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
             if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r;
         }
     }
+    CK_AT(9);
     tl_bar<TL_CONSUMERS>();  // S is reused by the next item of this CTA
+    CK_AT(10);
     if (tid == 0 && trace) trace[7] = gtime();   // outputs / partials stored
 }
+
+struct TlShared {
+    uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
+    float red[TL_SLOTS][TL_CW][2][16];
+    double ss_red[TL_CW];
+    TilePhase ph[3];
+};
 
 // Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Kept out of line so that its registers (two sets of B
 // fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
 // My tiles of slot k are band tiles TS * k + TPW * warp (+1 when TPW == 2); their block group advances by TS mod nbg per slot.
 template <int TYPE>
-__device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, int warp, int lane, uint32_t ring_u, uint32_t xfrag_u,
-                                        uint32_t corr_u, uint32_t full_u, uint32_t empty_u, uint32_t red_lane) {
+__device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, uint32_t ring_u, uint32_t sh_u) {
+    // (six arguments: they travel in registers; more of them went through the stack, i.e. through local memory in the hot loop)
     constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW, D_OFF = TileCfg<TYPE>::D_OFF;
+    const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
+    const uint32_t xfrag_u = ring_u + (uint32_t)TL_SLOTS * TL_SLOT_BYTES, corr_u = xfrag_u + (uint32_t)TL_XFRAG_BYTES;
+    const uint32_t full_u = sh_u + (uint32_t)offsetof(TlShared, full_bar), empty_u = sh_u + (uint32_t)offsetof(TlShared, empty_bar);
+    uint32_t red_lane = sh_u + (uint32_t)offsetof(TlShared, red) + (uint32_t)(warp * 2 * 16 + (lane >> 2)) * 4u;   // &red[0][warp][0][lane >> 2]
     const int g = lane >> 2, t = lane & 3;
     const bool xact = (t == (g >> 1));     // lane that holds B column g (block column g>>1, hi|lo = g&1)
+#if NL_TL_XB_SINGLE
+    uint32_t xb0[16];                      // B fragments of the tile at hand (one set: reloaded per tile, 16 registers fewer)
+#pragma unroll
+    for (int i = 0; i < 16; i++) xb0[i] = 0u;
+#define xb1 xb0
+#else
     uint32_t xb0[16], xb1[16];             // B fragments of my two tiles (reloaded only when the block group changes)
 #pragma unroll
     for (int i = 0; i < 16; i++) { xb0[i] = 0u; xb1[i] = 0u; }
+#endif
     const int t0 = TPW * warp, t1 = t0 + 1;   // my tiles of a slot (t1 only when TPW == 2)
     uint32_t tile_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
     uint32_t d_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)D_OFF + (uint32_t)lane * 4u;
@@ -453,6 +513,9 @@ __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, i
     int B = t0 - rg_of(t0, nbg, magic) * nbg;
     const int stepB = TS - rg_of(TS, nbg, magic) * nbg;
     int cb0 = -1, cb1 = -1;                // block groups whose fragments xb0 / xb1 hold
+#if NL_TL_XB_SINGLE
+#define cb1 cb0
+#endif
     for (int c0 = 0; c0 < band; c0 += TS, it++) {
         const uint32_t slot = (uint32_t)it % TL_SLOTS;
         const int n = min(TS, band - c0);
@@ -485,14 +548,154 @@ __device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, i
         if (lane == 0) mbar_arrive_u(empty_u + slot * 8u);
     }
     return it;
+#if NL_TL_XB_SINGLE
+#undef xb1
+#undef cb1
+#endif
 }
 
-struct TlShared {
-    uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
-    float red[TL_SLOTS][TL_CW][2][16];
-    double ss_red[TL_CW];
-    TilePhase ph[2];
-};
+// Phase input -> fp16 hi/lo B fragments in shared memory (xfrag) + per-block corrections (corr); returns this thread's part of the sum
+// of squares (RMSNorm).  mode 0: plain vector, 1: polled vector (looked at until no element reads as the sentinel), 2: tensor-parallel
+// exchange (xprev + the ranks' partials in rank order).  ckrow: optional clock64 stamps of tid 0 (slot 15: globaltimer of "first item valid").
+template <int TYPE, int mode>
+__device__ __forceinline__ double input_frags_body(const float *px, const float *pnw, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, int poll_ns,
+                                                   const float *xprev, float *xnext, const float *xparts, int tp, int dim, bool xstore, unsigned long long *ckrow) {
+    // One pass, no grid-wide reduction in front of the conversion: every 32-element block gets its own power-of-two scale S_b
+    // (max|y| * S_b in [2^10, 2^11), so 16 * y * S_b stays inside fp16 and the lo terms keep 10+ bits), applied back per block in
+    // tile_dot; the RMSNorm scale (one scalar per vector) is applied by the finishing warp to the finished sums:
+    // W . (inv * (x o w)) = inv * (W . (x o w)).  The float64 sum of squares is therefore off the critical path.
+    double ss = 0.0;
+    constexpr bool in_ll = mode == 1, in_exch = mode == 2;
+    const bool normed = pnw != nullptr;
+    float wv0[8];   // norm weights of my first item (items beyond the first only exist for dim > 4096: fetched where they are used)
+#pragma unroll
+    for (int i = 0; i < 8; i++) wv0[i] = 1.f;   // (defined on every path: left undefined, the compiler keeps the array in local memory)
+    if (normed && tid < nitem) {   // static data: requested before the first look at x
+        const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid + 1);
+        wv0[0] = a.x; wv0[1] = a.y; wv0[2] = a.z; wv0[3] = a.w; wv0[4] = b.x; wv0[5] = b.y; wv0[6] = b.z; wv0[7] = b.w;
+    }
+    // polled input: one item at a time, looked at until it is complete (items held across the loop were spilled to local memory, which is
+    // an L2 trip each with 12 KB of L1 left next to the ring; only 11008-column inputs have more than one item per thread anyway)
+#pragma unroll
+    for (int r = 0; r < TL_MAX_ITEMS; r++) {
+        const int q = tid + r * TL_CONSUMERS;          // item q = elements [8q, 8q+8); whole warps agree on q < nitem_pad + 31
+        if (r > 0 && (q & ~31) >= nitem_pad) break;     // (warp-uniform) nothing left for this warp: 4096-column inputs are one round
+        const bool store = q < nitem_pad;              // zero fragments for the padding blocks of the last block group
+        float y[8];
+#pragma unroll
+        for (int i = 0; i < 8; i++) y[i] = 0.f;
+        if (q < nitem) {
+            if (in_exch) {   // residual + every rank's partial of the row-split product, in rank order (the all-reduce)
+                const float4 a = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q + 1);
+                y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+                const float *parts = xparts;
+                for (int rr = 0; rr < tp; rr++) {
+                    const float4 c = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * dim) + 2 * q), d = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * dim) + 2 * q + 1);
+                    y[0] += c.x; y[1] += c.y; y[2] += c.z; y[3] += c.w; y[4] += d.x; y[5] += d.y; y[6] += d.z; y[7] += d.w;
+                }
+                if (xstore) {   // the new residual, read back at the next exchange
+                    reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
+                    reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
+                }
+            } else if (in_ll) {   // look again until none of my 8 elements reads as the sentinel
+                unsigned int xc[8];
+                ld_item(px, q, xc);
+                while (item_has_sent(xc)) {
+                    if (poll_ns) __nanosleep(poll_ns);
+                    ld_item(px, q, xc);
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) y[i] = __uint_as_float(xc[i]);
+                if (r == 0 && ckrow) { ckrow[2] = (unsigned long long)clock64(); ckrow[15] = gtime(); }
+            } else {
+                const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
+                y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
+            }
+            if (normed) {
+                float s4 = 0.f;
+                if (r == 0) {
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= wv0[i]; }
+                } else {
+                    const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q + 1);
+                    const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
+#pragma unroll
+                    for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= w[i]; }
+                }
+                ss += (double)s4;
+            }
+        }
+        float mx = 0.f;
+#pragma unroll
+        for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(y[i]));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the four lanes of a block sit next to each other
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        // Q4_0: max|y| * S in [2^10, 2^11) (the low-nibble operands carry 16 * y * S); Q8_0: [2^14, 2^15)
+        int es = (TYPE == NL_Q8_0 ? 268 : 264) - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+        es = es < 27 ? 27 : (es > 227 ? 227 : es);
+        const float S = __uint_as_float((uint32_t)es << 23);
+        const int b = q >> 2, o = (q & 3) * 8;         // block, offset of my 8 elements inside it
+        float bs = 0.f;
+        uint8_t *fb = xfrag + (size_t)(b >> 2) * 512 + (size_t)(2 * (b & 3)) * 64;
+        if constexpr (TYPE == NL_Q8_0) {
+            // MMA i takes elements 4i..4i+3: registers 2i = (e0, e2), 2i+1 = (e1, e3); my 8 elements fill registers o/2 .. o/2+3
+            float v[8];
+#pragma unroll
+            for (int j = 0; j < 8; j++) { v[j] = y[j] * S; bs += v[j]; }
+            uint32_t h[4], l[4];
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                h[2 * k] = pack_h2(v[4 * k], v[4 * k + 2]); h[2 * k + 1] = pack_h2(v[4 * k + 1], v[4 * k + 3]);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k])), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k + 1]));
+                l[2 * k] = pack_h2(v[4 * k] - f0.x, v[4 * k + 2] - f0.y); l[2 * k + 1] = pack_h2(v[4 * k + 1] - f1.x, v[4 * k + 3] - f1.y);
+            }
+            if (store) {
+                *reinterpret_cast<uint4 *>(fb + o * 2) = make_uint4(h[0], h[1], h[2], h[3]);          // hi column of this block
+                *reinterpret_cast<uint4 *>(fb + 64 + o * 2) = make_uint4(l[0], l[1], l[2], l[3]);     // lo column
+            }
+        } else {
+            const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
+#pragma unroll
+            for (int k = 0; k < 2; k++) {
+                float v[4];
+#pragma unroll
+                for (int j = 0; j < 4; j++) {
+                    v[j] = y[4 * k + j] * S;
+                    bs += v[j];
+                    if (pos == 0) v[j] *= 16.f;
+                }
+                const uint32_t h0 = pack_h2(v[0], v[2]), h1 = pack_h2(v[1], v[3]);
+                const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h1));
+                const uint32_t l0 = pack_h2(v[0] - f0.x, v[2] - f0.y), l1 = pack_h2(v[1] - f1.x, v[3] - f1.y);
+                const int reg = 4 * (ib + k) + 2 * pos;
+                if (store) {
+                    *reinterpret_cast<uint2 *>(fb + reg * 4) = make_uint2(h0, h1);         // hi column of this block
+                    *reinterpret_cast<uint2 *>(fb + 64 + reg * 4) = make_uint2(l0, l1);    // lo column
+                }
+            }
+        }
+        bs += __shfl_xor_sync(0xffffffffu, bs, 1);
+        bs += __shfl_xor_sync(0xffffffffu, bs, 2);
+        // per block: -zero_point * 2^-k * sum(y * S_b) (Q4_0: 8 * 2^-20, Q8_0: 128 * 2^-24 -- both 2^-17) and 2^k / S_b, which undoes
+        // the operand scaling (k = 20 | 24)
+        if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23));
+    }
+    return ss;
+}
+// Out-of-line entry points: the conversion gets its own register allocation (inlined into the phase loop the polled items were spilled
+// to local memory -- an L2 trip each with 12 KB of L1 left next to the ring); few arguments, so that they travel in registers.
+template <int TYPE>
+__device__ TL_FRAGS_CALL double input_frags(const float *px, const float *pnw, int polled, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, int poll_ns,
+                                           unsigned long long *ckrow) {
+    return polled ? input_frags_body<TYPE, 1>(px, pnw, nitem, nitem_pad, xfrag, corr, tid, poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow)
+                  : input_frags_body<TYPE, 0>(px, pnw, nitem, nitem_pad, xfrag, corr, tid, poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+}
+template <int TYPE>
+__device__ TL_FRAGS_CALL double input_frags_exch(const float *pnw, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, const float *xprev, float *xnext,
+                                                const float *xparts, int tp, int dim, bool xstore) {
+    return input_frags_body<TYPE, 2>(nullptr, pnw, nitem, nitem_pad, xfrag, corr, tid, 0, xprev, xnext, xparts, tp, dim, xstore, nullptr);
+}
+
 
 template <int TYPE>
 __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileArgs A) {
@@ -565,6 +768,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const int band = (u1 - u0) * urg * nbg;
             const int rg0 = u0 * urg;
             float racc = 0.f, gate = 0.f, post = 1.f;
+            if (lane == 0) TL_CK(p, 8);
             float best = -INFINITY;
             int best_i = 0x7fffffff;
             for (int c0 = 0; c0 < band; c0 += TS, it++) {
@@ -580,7 +784,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_poll(resid_src, r) : __ldcg(resid_src + r); }
                 }
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
-                if (lane == 0 && c1 == band) TL_TRACE(p, 5);   // last slot consumed by every math warp
+                if (lane == 0 && c1 == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
                 if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607: inv = 1 / sqrt(ss / n + eps) from the float64 sum of squares
                     double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);   // fixed butterfly order: deterministic
                     // float64 sum like the reference; the final 1/sqrt in fp32 (within 1 ulp of the reference's float32(1/sqrt(float64)))
@@ -655,7 +859,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 }
             }
             __syncwarp();
-            if (lane == 0) { TL_TRACE(p, 4); if (!poll) tl_arrive(A, p, cross != 0); TL_TRACE(p, 6); }   // polled outputs need no arrival
+            if (lane == 0) { TL_CK(p, 10); TL_TRACE(p, 4); if (!poll) tl_arrive(A, p, cross != 0); TL_TRACE(p, 6); }   // polled outputs need no arrival
             __syncwarp();
         }
         return;
@@ -672,19 +876,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     for (int p = 0; p < A.n_phases; p++) {
         if (warp == 1 && p + 1 < A.n_phases) {   // next descriptor while this phase runs: no L2 round trip after the barrier
             const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.phases[p + 1]);
-            uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.ph[(p + 1) & 1]);
+            uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.ph[(p + 1) % 3]);
             for (int i = lane; i < (int)(sizeof(TilePhase) / 4); i += 32) dst[i] = __ldg(src + i);
         }
         if (p == 0) tl_bar<TL_CONSUMERS>();
-        // every field of the descriptor is copied out before the last barrier of the prologue: warp 1 recycles the slot for phase
-        // p + 2 as soon as it gets there
-        const TilePhase &P = sh.ph[p & 1];
-        const int kind = P.kind, layer = P.layer, nbg = P.nbg, cols = P.cols;
+        // Three descriptor slots: warp 1 overwrites slot (p + 1) % 3, last read in phase p - 2, and every warp has left that phase (each
+        // iteration has a block barrier in front of its streaming loop).  So the fields are read from shared memory where they are used
+        // instead of being carried in registers across the phase (they were spilled to local memory: an L2 trip each, see input_frags).
+        const TilePhase &P = sh.ph[p % 3];
+        const int kind = P.kind, nbg = P.nbg;
         const unsigned int magic = P.nbg_magic;
-        const float *px = P.x, *pnw = P.norm_w;
-        const int in_ll = P.in_ll, in_exch = P.in_exch, wait_cross = P.wait_cross, xpar = P.par;
-        const float *xprev = P.prev;
-        float *xnext = P.next, *pout = P.out;
         int u0, u1;
         band_of(P.n_rg / P.unit_rg, blockIdx.x, G, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
@@ -698,15 +899,17 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             bool pre = false;
             if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
                 const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse);
-                attn_fetch(A.at.kcache + (size_t)layer * A.at.seq_len * kvd, A.at.vcache + (size_t)layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
+                attn_fetch(A.at.kcache + (size_t)P.layer * A.at.seq_len * kvd, A.at.vcache + (size_t)P.layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
                            min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
                 pre = true;
             }
-            if (tid == 0) { TL_TRACE(p, 0); if (!poll) tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
+            if (tid == 0) { TL_CK(p, 0); TL_TRACE(p, 0); if (!poll) tl_wait(A, p - 1, P.wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
             tl_bar<TL_CONSUMERS>();
+            if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(A.at, px, pout, layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p + 1u, poll,
-                                A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr);
+                attn_item_tiled(A.at, P.x, P.out, P.layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p + 1u, poll,
+                                A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr,
+                                (A.trace2 && item == (int)blockIdx.x) ? A.trace2 + ((size_t)blockIdx.x * A.n_phases + p) * 16 : nullptr);
                 pre = false;
             }
             if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
@@ -717,150 +920,40 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         }
 
         // ---- prologue: phase input -> fp16 hi/lo B fragments in shared memory ----
-        const bool normed = pnw != nullptr;
-        const int nitem = cols >> 3, nitem_pad = nbg * 16;
-        float wv0[8];   // norm weights of my first item: static data, requested before we wait for the producers of x (items beyond
-                        // the first only exist for dim > 4096: fetched where they are used, to keep the register count down)
-        if (normed && band > 0 && tid < nitem) {
-            const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * tid + 1);
-            wv0[0] = a.x; wv0[1] = a.y; wv0[2] = a.z; wv0[3] = a.w; wv0[4] = b.x; wv0[5] = b.y; wv0[6] = b.z; wv0[7] = b.w;
-        }
-        // polled input: first look at all of this thread's items at once (one L2 round trip when the producers are done), issued before
-        // the block barrier so that the trip overlaps the slowest math warp's last tiles
-        uint4 xa[TL_MAX_ITEMS][2];
-        if (in_ll && band > 0) {
-            if (tid == 0) TL_TRACE(p, 0);
-#pragma unroll
-            for (int r = 0; r < TL_MAX_ITEMS; r++) {
-                const int q = tid + r * TL_CONSUMERS;
-                if (q < nitem) { xa[r][0] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q); xa[r][1] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q + 1); }
-            }
-        }
+        if (tid == 0) TL_CK(p, 0);
+        if (P.in_ll && tid == 0) TL_TRACE(p, 0);
         if (p > 0) {
-            if (!poll && tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
+            if (!poll && tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, P.wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
             // also: every math warp is done with the previous phase's fragments (a polled element can be complete while a slower warp of
             // this CTA still streams the phase before), and warp 1's descriptor prefetch is ordered against its readers
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
-        // One pass, no grid-wide reduction in front of the conversion: every 32-element block gets its own power-of-two scale S_b
-        // (max|y| * S_b in [2^10, 2^11), so 16 * y * S_b stays inside fp16 and the lo terms keep 10+ bits), applied back per block in
-        // tile_dot; the RMSNorm scale (one scalar per vector) is applied by the finishing warp to the finished sums:
-        // W . (inv * (x o w)) = inv * (W . (x o w)).  The float64 sum of squares is therefore off the critical path.
-        double ss = 0.0;
-#pragma unroll
-        for (int r = 0; r < TL_MAX_ITEMS; r++) {
-            const int q = tid + r * TL_CONSUMERS;          // item q = elements [8q, 8q+8); whole warps agree on q < nitem_pad + 31
-            const bool store = q < nitem_pad;              // zero fragments for the padding blocks of the last block group
-            float y[8];
-#pragma unroll
-            for (int i = 0; i < 8; i++) y[i] = 0.f;
-            if (q < nitem) {
-                if (in_exch) {   // residual + every rank's partial of the row-split product, in rank order (the all-reduce)
-                    const float4 a = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(xprev) + 2 * q + 1);
-                    y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
-                    const float *parts = reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) + (size_t)xpar * A.tp * A.dim;
-                    for (int rr = 0; rr < A.tp; rr++) {
-                        const float4 c = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * A.dim) + 2 * q), d = __ldcg(reinterpret_cast<const float4 *>(parts + (size_t)rr * A.dim) + 2 * q + 1);
-                        y[0] += c.x; y[1] += c.y; y[2] += c.z; y[3] += c.w; y[4] += d.x; y[5] += d.y; y[6] += d.z; y[7] += d.w;
-                    }
-                    if (u0 == 0) {   // (the CTA that holds the matrix's first unit) the new residual, read back at the next exchange
-                        reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
-                        reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
-                    }
-                } else if (in_ll) {   // look again until none of my 8 elements reads as the sentinel
-                    while (has_sent(xa[r][0], xa[r][1])) {
-                        if (A.poll_ns) __nanosleep(A.poll_ns);
-                        xa[r][0] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q); xa[r][1] = ld_vol_v4(reinterpret_cast<const uint4 *>(px) + 2 * q + 1);
-                    }
-                    y[0] = __uint_as_float(xa[r][0].x); y[1] = __uint_as_float(xa[r][0].y); y[2] = __uint_as_float(xa[r][0].z); y[3] = __uint_as_float(xa[r][0].w);
-                    y[4] = __uint_as_float(xa[r][1].x); y[5] = __uint_as_float(xa[r][1].y); y[6] = __uint_as_float(xa[r][1].z); y[7] = __uint_as_float(xa[r][1].w);
-                    if (tid == 0 && r == 0) TL_TRACE(p, 1);
-                } else {
-                    const float4 a = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q), b = __ldcg(reinterpret_cast<const float4 *>(px) + 2 * q + 1);
-                    y[0] = a.x; y[1] = a.y; y[2] = a.z; y[3] = a.w; y[4] = b.x; y[5] = b.y; y[6] = b.z; y[7] = b.w;
-                }
-                if (normed) {
-                    float s4 = 0.f;
-                    if (r == 0) {
-#pragma unroll
-                        for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= wv0[i]; }
-                    } else {
-                        const float4 a = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q), b = __ldg(reinterpret_cast<const float4 *>(pnw) + 2 * q + 1);
-                        const float w[8] = {a.x, a.y, a.z, a.w, b.x, b.y, b.z, b.w};
-#pragma unroll
-                        for (int i = 0; i < 8; i++) { s4 = fmaf(y[i], y[i], s4); y[i] *= w[i]; }
-                    }
-                    ss += (double)s4;
-                }
-            }
-            float mx = 0.f;
-#pragma unroll
-            for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(y[i]));
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the four lanes of a block sit next to each other
-            mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
-            // Q4_0: max|y| * S in [2^10, 2^11) (the low-nibble operands carry 16 * y * S); Q8_0: [2^14, 2^15)
-            int es = (TYPE == NL_Q8_0 ? 268 : 264) - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
-            es = es < 27 ? 27 : (es > 227 ? 227 : es);
-            const float S = __uint_as_float((uint32_t)es << 23);
-            const int b = q >> 2, o = (q & 3) * 8;         // block, offset of my 8 elements inside it
-            float bs = 0.f;
-            uint8_t *fb = xfrag + (size_t)(b >> 2) * 512 + (size_t)(2 * (b & 3)) * 64;
-            if constexpr (TYPE == NL_Q8_0) {
-                // MMA i takes elements 4i..4i+3: registers 2i = (e0, e2), 2i+1 = (e1, e3); my 8 elements fill registers o/2 .. o/2+3
-                float v[8];
-#pragma unroll
-                for (int j = 0; j < 8; j++) { v[j] = y[j] * S; bs += v[j]; }
-                uint32_t h[4], l[4];
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    h[2 * k] = pack_h2(v[4 * k], v[4 * k + 2]); h[2 * k + 1] = pack_h2(v[4 * k + 1], v[4 * k + 3]);
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k])), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h[2 * k + 1]));
-                    l[2 * k] = pack_h2(v[4 * k] - f0.x, v[4 * k + 2] - f0.y); l[2 * k + 1] = pack_h2(v[4 * k + 1] - f1.x, v[4 * k + 3] - f1.y);
-                }
-                if (store) {
-                    *reinterpret_cast<uint4 *>(fb + o * 2) = make_uint4(h[0], h[1], h[2], h[3]);          // hi column of this block
-                    *reinterpret_cast<uint4 *>(fb + 64 + o * 2) = make_uint4(l[0], l[1], l[2], l[3]);     // lo column
-                }
-            } else {
-                const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
-#pragma unroll
-                for (int k = 0; k < 2; k++) {
-                    float v[4];
-#pragma unroll
-                    for (int j = 0; j < 4; j++) {
-                        v[j] = y[4 * k + j] * S;
-                        bs += v[j];
-                        if (pos == 0) v[j] *= 16.f;
-                    }
-                    const uint32_t h0 = pack_h2(v[0], v[2]), h1 = pack_h2(v[1], v[3]);
-                    const float2 f0 = __half22float2(*reinterpret_cast<const __half2 *>(&h0)), f1 = __half22float2(*reinterpret_cast<const __half2 *>(&h1));
-                    const uint32_t l0 = pack_h2(v[0] - f0.x, v[2] - f0.y), l1 = pack_h2(v[1] - f1.x, v[3] - f1.y);
-                    const int reg = 4 * (ib + k) + 2 * pos;
-                    if (store) {
-                        *reinterpret_cast<uint2 *>(fb + reg * 4) = make_uint2(h0, h1);         // hi column of this block
-                        *reinterpret_cast<uint2 *>(fb + 64 + reg * 4) = make_uint2(l0, l1);    // lo column
-                    }
-                }
-            }
-            bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-            bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-            // per block: -zero_point * 2^-k * sum(y * S_b) (Q4_0: 8 * 2^-20, Q8_0: 128 * 2^-24 -- both 2^-17) and 2^k / S_b, which undoes
-            // the operand scaling (k = 20 | 24)
-            if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23));
-        }
+        if (tid == 0) TL_CK(p, 1);
+        // (out of line: its registers are allocated for the conversion alone; inlined into the phase loop it spilled the polled
+        // items to local memory, which is an L2 trip each with 12 KB of L1 left next to the ring)
+        const bool normed = P.norm_w != nullptr, in_exch = P.in_exch != 0;
+        const int nitem = P.cols >> 3, nitem_pad = nbg * 16;
+        const bool xstore = in_exch && u0 == 0;   // (the CTA that holds the matrix's first unit) stores the new residual
+        const float *xparts = in_exch ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) + (size_t)P.par * A.tp * A.dim : nullptr;
+        unsigned long long *ckrow = (A.trace2 && tid == 0) ? A.trace2 + ((size_t)blockIdx.x * A.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
+        double ss = in_exch ? input_frags_exch<TYPE>(P.norm_w, nitem, nitem_pad, xfrag, corr, tid, P.prev, P.next, xparts, A.tp, A.dim, xstore)
+                            : input_frags<TYPE>(P.x, P.norm_w, P.in_ll, nitem, nitem_pad, xfrag, corr, tid, A.poll_ns, ckrow);
+        if (ckrow && A.trace && P.in_ll) A.trace[((size_t)blockIdx.x * A.n_phases + p) * 8 + 1] = ckrow[15];   // "first item valid" (globaltimer)
+        if (tid == 0) TL_CK(p, 3);
+        if (tid == TL_CONSUMERS - 32) TL_CK(p, 6);
         if (normed) {
             ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
             if (lane == 0) sh.ss_red[warp] = ss;
         }
         tl_bar<TL_CONSUMERS>();   // fragments complete; the finishing warp turns ss_red into the RMSNorm scale once the first slot is consumed
-        if (tid == 0) TL_TRACE(p, 2);
+        if (tid == 0) { TL_TRACE(p, 2); TL_CK(p, 4); }
 
         // ---- stream the band ----
-        if (in_exch && u0 == 0) __threadfence();
-        it = stream_band<TYPE>(band, nbg, magic, it, warp, lane, smem_u32(ring), smem_u32(xfrag), smem_u32(corr), smem_u32(&sh.full_bar[0]),
-                         smem_u32(&sh.empty_bar[0]), smem_u32(&sh.red[0][warp][0][lane >> 2]));
-        if (tid == 0) TL_TRACE(p, 3);
+        if (xstore) __threadfence();
+        it = stream_band<TYPE>(band, nbg, magic, it, smem_u32(ring), smem_u32(&sh));
+        if (tid == 0) { TL_TRACE(p, 3); TL_CK(p, 5); }
+        if (tid == TL_CONSUMERS - 32) TL_CK(p, 7);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
     if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);

@@ -106,6 +106,7 @@ struct TileArgs {
     int att_chunk;            // attention: positions per split while the splits last (<= 96 = one pass)
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
+    unsigned long long *trace2; // optional: [cta][phase][16] clock64 stamps (tools/trace_fine.py)
 };
 
 // planar (qs, d) -> tiles: row group R of the source lands at tile row group rg_off + R * rg_stride (gate/up interleave: stride 2,
