@@ -407,7 +407,8 @@ static int build_mega(nl_model *m) {
 
 // ---- tiled tensor-core decode path (nl_tile.cuh) ----
 static bool tile_eligible(const DevMat &w) {
-    return (w.type == NL_Q4_0 || w.type == NL_Q8_0) && w.rows % 16 == 0 && w.cols % 32 == 0 && w.cols <= (int64_t)TL_MAX_NBG * 128 && w.rows * (w.cols / 32) < (1ll << 31);
+    return (w.type == NL_Q4_0 || w.type == NL_Q8_0) && w.rows % 16 == 0 && w.cols % 32 == 0 && w.cols <= (int64_t)TL_MAX_NBG * 128 && w.rows * (w.cols / 32) < (1ll << 31) &&
+           w.rows < (1ll << 20);   // (band_of: row groups x grid^2 < 2^32)
 }
 // Builds one tiled matrix from `n` planar matrices of equal cols: concatenated row-wise (interleave = false) or with their
 // 16-row groups interleaved (gate/up: group i of mats[0], group i of mats[1], ...).
@@ -428,7 +429,7 @@ static int make_tiles(uint8_t **dst, const DevMat *const *mats, int n, bool inte
 static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const void *x, int in_ll,
                             const float *norm_w, const float *bias, void *out, int out_ll, const void *resid = nullptr, int resid_ll = 0) {
     memset(&P, 0, sizeof P);
-    P.kind = PH_GEMV; P.tiles = tiles; P.n_rg = n_rg; P.nbg = (cols / 32 + 3) / 4; P.nbg_magic = tile_magic(P.nbg); P.unit_rg = unit_rg;
+    P.kind = PH_GEMV; P.tiles = tiles; P.n_rg = n_rg; P.nbg = (cols / 32 + 3) / 4; P.nbg_magic = tile_magic(P.nbg); P.unit_rg = unit_rg; P.units = n_rg / unit_rg;
     P.cols = cols; P.rows = rows; P.epi = epi; P.x = (const float *)x; P.norm_w = norm_w; P.bias = bias; P.out = (float *)out;
     P.resid = (const float *)resid; P.in_ll = in_ll; P.out_ll = out_ll; P.resid_ll = resid_ll;
 }
@@ -559,7 +560,7 @@ static int build_tiled(nl_model *m) {
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
     a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = LL;
-    a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.amax = m->amax; m->amax_valid = true;
+    a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.att_hpi = tile_env_int("NL_ATT_HPI", 0, 0, 64); a.amax = m->amax; m->amax_valid = true;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;

@@ -63,9 +63,13 @@ __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
     return *reinterpret_cast<const uint32_t *>(&h);
 }
 template <int NT> __device__ __forceinline__ void tl_bar() { asm volatile("bar.sync 1, %0;" ::"n"(NT) : "memory"); }
-__device__ __forceinline__ void band_of(int units, int b, int G, int &u0, int &u1) {
-    u0 = (int)(((long long)units * b) / G);
-    u1 = (int)(((long long)units * (b + 1)) / G);
+// CTA b's share [u0, u1) of `units` distribution units: floor(units * b / G) without a divide (three roles evaluate this per phase, the
+// math warps on the critical path; a 64-bit divide is a subroutine of hundreds of cycles).  gmagic = ceil(2^32 / G), exact while
+// units * (b + 1) < 2^32 / G (launch_tiled checks the bound); G == 1 keeps everything.
+__device__ __forceinline__ void band_of(int units, int b, int G, unsigned int gmagic, int &u0, int &u1) {
+    if (G == 1) { u0 = 0; u1 = units; return; }
+    u0 = (int)__umulhi((unsigned)(units * b), gmagic);
+    u1 = (int)__umulhi((unsigned)(units * (b + 1)), gmagic);
 }
 // tile index inside a band -> row group (magic = ceil(2^32 / nbg); exact for r < 2^32 / nbg)
 __device__ __forceinline__ int rg_of(int r, int nbg, unsigned int magic) { return nbg == 1 ? r : (int)__umulhi((unsigned)r, magic); }
@@ -93,6 +97,22 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
 #define TL_FRAGS_CALL __forceinline__
 #else
 #define TL_FRAGS_CALL __noinline__
+#endif
+#ifndef NL_TL_STREAM_INLINE
+#define NL_TL_STREAM_INLINE 1
+#endif
+#if NL_TL_STREAM_INLINE
+#define TL_STREAM_CALL __forceinline__
+#else
+#define TL_STREAM_CALL __noinline__
+#endif
+#ifndef NL_TL_ATTN_INLINE
+#define NL_TL_ATTN_INLINE 0
+#endif
+#if NL_TL_ATTN_INLINE
+#define TL_ATTN_CALL __forceinline__
+#else
+#define TL_ATTN_CALL __noinline__
 #endif
 #ifndef NL_TL_XB_SINGLE
 #define NL_TL_XB_SINGLE 1
@@ -128,6 +148,13 @@ __device__ __forceinline__ float ld_poll(const float *base, int idx) {
         asm volatile("ld.relaxed.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(base + idx) : "memory");
     } while (v == TL_SENT);
     return __uint_as_float(v);
+}
+__device__ __forceinline__ void ld_poll2(const float *base, int i0, int i1, float &v0, float &v1) {   // both looks in flight together
+    unsigned int a, b;
+    do {
+        asm volatile("ld.relaxed.gpu.global.u32 %0, [%2];\n\tld.relaxed.gpu.global.u32 %1, [%3];" : "=r"(a), "=r"(b) : "l"(base + i0), "l"(base + i1) : "memory");
+    } while (a == TL_SENT || b == TL_SENT);
+    v0 = __uint_as_float(a); v1 = __uint_as_float(b);
 }
 __device__ __forceinline__ uint4 ld_vol_v4(const void *p) {
     uint4 v;
@@ -283,10 +310,32 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
-struct AttnItem { int kvh, sp, nse, t_begin, t_end; };
-__device__ __forceinline__ AttnItem attn_locate(const MegaAttn &at, int item, int n, int nse) {
+struct TlShared {
+    uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
+    float red[TL_SLOTS][TL_CW][2][16];
+    double ss_red[TL_CW];
+    TilePhase ph[3];
+    MegaAttn at;              // copy of TileArgs::at: out-of-line device functions cannot take the address of a kernel parameter for free
+    unsigned long long *trace, *trace2;   // (same: TileArgs::trace / trace2, n_phases, poll_ns, tp, dim)
+    const float *ar_mine;     // tensor parallel: this rank's exchange area
+    int n_phases, poll_ns, tp, dim;
+};
+
+// item = (hpi consecutive q heads of one kv head, split of the positions).  hpi = the whole GQA group shares one pass over the K/V rows;
+// smaller hpi (attn_hpi) spreads a short context over more CTAs -- the rows come from L2 anyway and an item's time is per-head work.
+struct AttnItem { int kvh, h0, nh, wr, sp, nse, t_begin, t_end; };
+__device__ __forceinline__ int attn_hpi(const MegaAttn &at, int nse, int G, int forced) {
+    const int group = at.n_heads / at.n_kv_heads;
+    if (forced > 0) return forced >= group || group % forced ? group : forced;
+    for (int hpi = 1; hpi < group; hpi++)
+        if (group % hpi == 0 && (at.n_heads / hpi) * nse <= G) return hpi;
+    return group;
+}
+__device__ __forceinline__ AttnItem attn_locate(const MegaAttn &at, int item, int n, int nse, int hpi) {
     AttnItem I;
-    I.kvh = item / nse; I.sp = item - I.kvh * nse; I.nse = nse;
+    const int group = at.n_heads / at.n_kv_heads, vk = item / nse;
+    I.h0 = vk * hpi; I.nh = hpi; I.kvh = I.h0 / group; I.wr = (I.h0 - I.kvh * group) == 0;   // one item per kv head writes the new K/V row
+    I.sp = item - vk * nse; I.nse = nse;
     const int per = (n + nse - 1) / nse;
     I.t_begin = min(I.sp * per, n); I.t_end = min(I.t_begin + per, n);
     return I;
@@ -303,11 +352,17 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
 }
 
 // qkv: this layer's q | k | v vector (polled element by element when `poll`), ao: its attention output
-__device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float *qkv, float *ao, int layer, const AttnItem I, int pos, bool prefetched,
-                                                AttnT &S, int tid, unsigned int oflag, bool poll, unsigned long long *trace, unsigned long long *ck) {
-    if (tid != 0) ck = nullptr;
+// (few scalar arguments: they travel in registers; the rest is read from shared memory)
+__device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, const float *qkv, float *ao, AttnT &S, int layer, int item, int nse, int hpi, int pos, int p,
+                                             bool prefetched, bool poll, unsigned int oflag) {
+    const MegaAttn &at = sh.at;
+    const int tid = threadIdx.x;
+    const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
+    unsigned long long *trace = (sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+    unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
+    (void)ck;
     constexpr int HD = 64, HALF = 32;
-    const int group = at.n_heads / at.n_kv_heads, kvd = at.n_kv_heads * HD;
+    const int group = I.nh, kvd = at.n_kv_heads * HD;   // "group": the q heads of THIS item (I.h0 .. I.h0 + group - 1)
     const int warp = tid >> 5, lane = tid & 31;
     const int kvh = I.kvh;
     float *kc = at.kcache + (size_t)layer * at.seq_len * kvd, *vc = at.vcache + (size_t)layer * at.seq_len * kvd;
@@ -318,8 +373,10 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         const int hh = tid >> 5, i = tid & 31;
         const bool isk = hh == group;
         // q | k | v are one vector [H*hd + 2*kvd] (at.q = base; at.k / at.v are element offsets from it)
-        const int e0 = isk ? (int)(at.k - at.q) + kvh * HD : (kvh * group + hh) * HD;
-        const float x0 = poll ? ld_poll(qkv, e0 + i) : __ldcg(qkv + e0 + i), x1 = poll ? ld_poll(qkv, e0 + i + HALF) : __ldcg(qkv + e0 + i + HALF);
+        const int e0 = isk ? (int)(at.k - at.q) + kvh * HD : (I.h0 + hh) * HD;
+        float x0, x1;
+        if (poll) ld_poll2(qkv, e0 + i, e0 + i + HALF, x0, x1);
+        else { x0 = __ldcg(qkv + e0 + i); x1 = __ldcg(qkv + e0 + i + HALF); }
         const float c = __ldg(at.cos_t + (size_t)pos * HALF + i), sn = __ldg(at.sin_t + (size_t)pos * HALF + i);
         float r0, r1;
         if (!at.conj) { r0 = x0 * c - x1 * sn; r1 = x0 * sn + x1 * c; }
@@ -346,7 +403,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         tl_bar<TL_CONSUMERS>();
     }
     CK_AT(3);
-    if (owner && tid < HD) {   // KV write, go/model.go:552-554
+    if (owner && I.wr && tid < HD) {   // KV write, go/model.go:552-554
         kc[(size_t)pos * kvd + kvh * HD + tid] = S.knew[tid];
         vc[(size_t)pos * kvd + kvh * HD + tid] = S.vnew[tid];
     }
@@ -372,13 +429,24 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
             for (int tl = tid >> 3; tl < ((cn + 3) & ~3); tl += TL_CONSUMERS / 8) {   // a warp covers 4 consecutive positions: whole warps agree
                 float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
                 if (tl < cn) { k0 = *reinterpret_cast<const float4 *>(&S.Ks[tl][4 * sub]); k1 = *reinterpret_cast<const float4 *>(&S.Ks[tl][32 + 4 * sub]); }
-                for (int h2 = 0; h2 < group; h2++) {
-                    const float4 q0 = *reinterpret_cast<const float4 *>(&S.q[h2][4 * sub]), q1 = *reinterpret_cast<const float4 *>(&S.q[h2][32 + 4 * sub]);
-                    float d = (fmaf(q0.x, k0.x, q0.y * k0.y) + fmaf(q0.z, k0.z, q0.w * k0.w)) + (fmaf(q1.x, k1.x, q1.y * k1.y) + fmaf(q1.z, k1.z, q1.w * k1.w));
-                    d += __shfl_xor_sync(0xffffffffu, d, 1);
-                    d += __shfl_xor_sync(0xffffffffu, d, 2);
-                    d += __shfl_xor_sync(0xffffffffu, d, 4);
-                    if (sub == 0 && tl < cn) S.p[h2][tl] = d * at.scale;
+                float d[MG_MAX_GROUP];   // all heads' partial dots first, then their shuffle chains side by side
+#pragma unroll
+                for (int h2 = 0; h2 < MG_MAX_GROUP; h2++) {
+                    d[h2] = 0.f;
+                    if (h2 < group) {
+                        const float4 q0 = *reinterpret_cast<const float4 *>(&S.q[h2][4 * sub]), q1 = *reinterpret_cast<const float4 *>(&S.q[h2][32 + 4 * sub]);
+                        d[h2] = (fmaf(q0.x, k0.x, q0.y * k0.y) + fmaf(q0.z, k0.z, q0.w * k0.w)) + (fmaf(q1.x, k1.x, q1.y * k1.y) + fmaf(q1.z, k1.z, q1.w * k1.w));
+                    }
+                }
+#pragma unroll
+                for (int h2 = 0; h2 < MG_MAX_GROUP; h2++) {
+                    if (h2 < group) {   // (uniform)
+                        float v = d[h2];
+                        v += __shfl_xor_sync(0xffffffffu, v, 1);
+                        v += __shfl_xor_sync(0xffffffffu, v, 2);
+                        v += __shfl_xor_sync(0xffffffffu, v, 4);
+                        if (sub == 0 && tl < cn) S.p[h2][tl] = v * at.scale;
+                    }
                 }
             }
         }
@@ -426,7 +494,7 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
         const int hh = tid >> 6, dd = tid & 63;            // (shadows the PV mapping)
         float o = 0.f;
         for (int pp = 0; pp < nparts; pp++) o += pvs[(pp * pthreads + hh * 16 + (dd >> 2)) * 4 + (dd & 3)];
-        const int h = kvh * group + hh;
+        const int h = I.h0 + hh;
         float M = S.m_run[hh], den = S.l_run[hh];
         if (I.nse > 1) {
             // un-normalised partials travel as flagged {value, flag} pairs: split 0 folds the others as they land (fixed order =>
@@ -475,18 +543,12 @@ __device__ __forceinline__ void attn_item_tiled(const MegaAttn &at, const float 
     if (tid == 0 && trace) trace[7] = gtime();   // outputs / partials stored
 }
 
-struct TlShared {
-    uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
-    float red[TL_SLOTS][TL_CW][2][16];
-    double ss_red[TL_CW];
-    TilePhase ph[3];
-};
 
-// Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Kept out of line so that its registers (two sets of B
+// Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Inlined into gemv_phase (out of line there), so that its registers (the B
 // fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
 // My tiles of slot k are band tiles TS * k + TPW * warp (+1 when TPW == 2); their block group advances by TS mod nbg per slot.
 template <int TYPE>
-__device__ __noinline__ int stream_band(int band, int nbg, unsigned int magic, int it, uint32_t ring_u, uint32_t sh_u) {
+__device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic, int it, uint32_t ring_u, uint32_t sh_u) {
     // (six arguments: they travel in registers; more of them went through the stack, i.e. through local memory in the hot loop)
     constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW, D_OFF = TileCfg<TYPE>::D_OFF;
     const int warp = threadIdx.x >> 5, lane = threadIdx.x & 31;
@@ -682,20 +744,52 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
     }
     return ss;
 }
-// Out-of-line entry points: the conversion gets its own register allocation (inlined into the phase loop the polled items were spilled
-// to local memory -- an L2 trip each with 12 KB of L1 left next to the ring); few arguments, so that they travel in registers.
+// One GEMV phase on the math warps, after the wait for its input: input vector -> fragments, then the streaming loop.  ONE out-of-line
+// function per phase kind (this one and attn_item_tiled) with the conversion and the loop inlined into it: its registers are allocated
+// for the phase alone, and the phase loop of the kernel keeps almost nothing alive across the call.  Anything spilled around here goes to
+// local memory, i.e. to L2 (12 KB of L1 are left next to the ring): measured 2x on the whole token when the hot loop spilled its B
+// fragments.  Everything the phase needs beyond the six scalar arguments is read from shared memory.
 template <int TYPE>
-__device__ TL_FRAGS_CALL double input_frags(const float *px, const float *pnw, int polled, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, int poll_ns,
-                                           unsigned long long *ckrow) {
-    return polled ? input_frags_body<TYPE, 1>(px, pnw, nitem, nitem_pad, xfrag, corr, tid, poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow)
-                  : input_frags_body<TYPE, 0>(px, pnw, nitem, nitem_pad, xfrag, corr, tid, poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+__device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t *smem, int band, bool first_unit, int it, int p) {
+    const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
+    uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
+    float2 *corr = reinterpret_cast<float2 *>(xfrag + TL_XFRAG_BYTES);
+    const int nbg = P.nbg;
+    const bool normed = P.norm_w != nullptr, in_exch = P.in_exch != 0;
+    const int nitem = P.cols >> 3, nitem_pad = nbg * 16;
+    const bool xstore = in_exch && first_unit;   // (the CTA that holds the matrix's first unit) stores the new residual
+    unsigned long long *ckrow = (sh.trace2 && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
+    unsigned long long *trrow = (sh.trace && tid == 0) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+#if NL_TL_FINE_TRACE
+    if (ckrow) ckrow[1] = (unsigned long long)clock64();
+#endif
+    double ss;
+    if (in_exch) ss = input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
+    else if (P.in_ll) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    else ss = input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    if (trrow && ckrow && P.in_ll) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
+#if NL_TL_FINE_TRACE
+    if (ckrow) ckrow[3] = (unsigned long long)clock64();
+    if (tid == TL_CONSUMERS - 32 && sh.trace2) sh.trace2[((size_t)blockIdx.x * sh.n_phases + p) * 16 + 6] = (unsigned long long)clock64();
+#endif
+    if (normed) {
+        ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
+        if (lane == 0) sh.ss_red[warp] = ss;
+    }
+    tl_bar<TL_CONSUMERS>();   // fragments complete; the finishing warp turns ss_red into the RMSNorm scale once the first slot is consumed
+    if (trrow) trrow[2] = gtime();
+#if NL_TL_FINE_TRACE
+    if (ckrow) ckrow[4] = (unsigned long long)clock64();
+#endif
+    if (xstore) __threadfence();
+    it = stream_band<TYPE>(band, nbg, P.nbg_magic, it, smem_u32(smem), smem_u32(&sh));
+    if (trrow) trrow[3] = gtime();
+#if NL_TL_FINE_TRACE
+    if (ckrow) ckrow[5] = (unsigned long long)clock64();
+    if (tid == TL_CONSUMERS - 32 && sh.trace2) sh.trace2[((size_t)blockIdx.x * sh.n_phases + p) * 16 + 7] = (unsigned long long)clock64();
+#endif
+    return it;
 }
-template <int TYPE>
-__device__ TL_FRAGS_CALL double input_frags_exch(const float *pnw, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, const float *xprev, float *xnext,
-                                                const float *xparts, int tp, int dim, bool xstore) {
-    return input_frags_body<TYPE, 2>(nullptr, pnw, nitem, nitem_pad, xfrag, corr, tid, 0, xprev, xnext, xparts, tp, dim, xstore, nullptr);
-}
-
 
 template <int TYPE>
 __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileArgs A) {
@@ -712,7 +806,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     const unsigned int epoch = A.epoch ? __ldg(A.epoch) : 0u;
     const unsigned int flag_base = epoch * (unsigned)(A.n_phases + 1);
     const bool poll = A.poll != 0;
+    if (warp == 1) {
+        const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.at);
+        for (int i = lane; i < (int)(sizeof(MegaAttn) / 4); i += 32) reinterpret_cast<uint32_t *>(&sh.at)[i] = src[i];
+    }
     if (tid == 0) {
+        sh.trace = A.trace; sh.trace2 = A.trace2; sh.n_phases = A.n_phases; sh.poll_ns = A.poll_ns; sh.tp = A.tp; sh.dim = A.dim;
+        sh.ar_mine = A.tp > 1 ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) : nullptr;
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -729,7 +829,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             if (__ldg(&P->kind) != PH_GEMV) continue;
             const int nbg = __ldg(&P->nbg), urg = __ldg(&P->unit_rg);
             int u0, u1;
-            band_of(__ldg(&P->n_rg) / urg, blockIdx.x, G, u0, u1);
+            band_of(__ldg(&P->units), blockIdx.x, G, A.g_magic, u0, u1);
             const int band = (u1 - u0) * urg * nbg;
             const uint8_t *src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TILE;
             for (int c0 = 0; c0 < band; c0 += TS, it++) {
@@ -764,7 +864,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
             const int cols_p = __ldg(&P->cols);
             int u0, u1;
-            band_of(__ldg(&P->n_rg) / urg, blockIdx.x, G, u0, u1);
+            band_of(__ldg(&P->units), blockIdx.x, G, A.g_magic, u0, u1);
             const int band = (u1 - u0) * urg * nbg;
             const int rg0 = u0 * urg;
             float racc = 0.f, gate = 0.f, post = 1.f;
@@ -887,18 +987,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         const int kind = P.kind, nbg = P.nbg;
         const unsigned int magic = P.nbg_magic;
         int u0, u1;
-        band_of(P.n_rg / P.unit_rg, blockIdx.x, G, u0, u1);
+        band_of(P.units, blockIdx.x, G, A.g_magic, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
         if (kind == PH_ATTN) {
             tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
             const int pos = *A.at.pos, n = pos + 1;
             int nse = (n + A.att_chunk - 1) / A.att_chunk;   // one prefetched pass (att_chunk <= 96 positions) per split while the splits last
             nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
-            const int n_items = A.at.n_kv_heads * nse;
+            const int hpi = attn_hpi(A.at, nse, G, A.att_hpi);
+            const int n_items = (A.at.n_heads / hpi) * nse;
             const int kvd = A.at.n_kv_heads * 64;
             bool pre = false;
             if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
-                const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse);
+                const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse, hpi);
                 attn_fetch(A.at.kcache + (size_t)P.layer * A.at.seq_len * kvd, A.at.vcache + (size_t)P.layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
                            min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
                 pre = true;
@@ -907,9 +1008,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
             if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(A.at, P.x, P.out, P.layer, attn_locate(A.at, item, n, nse), pos, pre, att, tid, flag_base + (unsigned)p + 1u, poll,
-                                A.trace ? A.trace + ((size_t)blockIdx.x * A.n_phases + p) * 8 : nullptr,
-                                (A.trace2 && item == (int)blockIdx.x) ? A.trace2 + ((size_t)blockIdx.x * A.n_phases + p) * 16 : nullptr);
+                attn_item_tiled(sh, P.x, P.out, att, P.layer, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
                 pre = false;
             }
             if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
@@ -929,43 +1028,21 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
-        if (tid == 0) TL_CK(p, 1);
-        // (out of line: its registers are allocated for the conversion alone; inlined into the phase loop it spilled the polled
-        // items to local memory, which is an L2 trip each with 12 KB of L1 left next to the ring)
-        const bool normed = P.norm_w != nullptr, in_exch = P.in_exch != 0;
-        const int nitem = P.cols >> 3, nitem_pad = nbg * 16;
-        const bool xstore = in_exch && u0 == 0;   // (the CTA that holds the matrix's first unit) stores the new residual
-        const float *xparts = in_exch ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) + (size_t)P.par * A.tp * A.dim : nullptr;
-        unsigned long long *ckrow = (A.trace2 && tid == 0) ? A.trace2 + ((size_t)blockIdx.x * A.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
-        double ss = in_exch ? input_frags_exch<TYPE>(P.norm_w, nitem, nitem_pad, xfrag, corr, tid, P.prev, P.next, xparts, A.tp, A.dim, xstore)
-                            : input_frags<TYPE>(P.x, P.norm_w, P.in_ll, nitem, nitem_pad, xfrag, corr, tid, A.poll_ns, ckrow);
-        if (ckrow && A.trace && P.in_ll) A.trace[((size_t)blockIdx.x * A.n_phases + p) * 8 + 1] = ckrow[15];   // "first item valid" (globaltimer)
-        if (tid == 0) TL_CK(p, 3);
-        if (tid == TL_CONSUMERS - 32) TL_CK(p, 6);
-        if (normed) {
-            ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
-            if (lane == 0) sh.ss_red[warp] = ss;
-        }
-        tl_bar<TL_CONSUMERS>();   // fragments complete; the finishing warp turns ss_red into the RMSNorm scale once the first slot is consumed
-        if (tid == 0) { TL_TRACE(p, 2); TL_CK(p, 4); }
-
-        // ---- stream the band ----
-        if (xstore) __threadfence();
-        it = stream_band<TYPE>(band, nbg, magic, it, smem_u32(ring), smem_u32(&sh));
-        if (tid == 0) { TL_TRACE(p, 3); TL_CK(p, 5); }
-        if (tid == TL_CONSUMERS - 32) TL_CK(p, 7);
+        it = gemv_phase<TYPE>(sh, P, smem, band, u0 == 0, it, p);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
     if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
 }
 
 template <int TYPE>
-static int launch_tiled_t(const TileArgs &a, int grid, cudaStream_t st) {
+static int launch_tiled_t(const TileArgs &a_in, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
         if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
         configured = true;
     }
+    TileArgs a = a_in;
+    a.g_magic = grid <= 1 ? 0u : (unsigned int)(((1ull << 32) + (unsigned)grid - 1) / (unsigned)grid);
     cudaLaunchConfig_t cfg{};
     cfg.gridDim = dim3(grid); cfg.blockDim = dim3(TL_THREADS); cfg.dynamicSmemBytes = TL_DYN_SMEM; cfg.stream = st;
     cudaLaunchAttribute at[1];

@@ -68,6 +68,7 @@ struct TilePhase {
     int n_rg, nbg;
     unsigned int nbg_magic;   // ceil(2^32 / nbg): tile index -> row group without a divide
     int unit_rg;              // row groups per distribution unit (2 for gate/up: gate group, then the up group of the same rows)
+    int units;                // n_rg / unit_rg: what the CTAs share out (must stay below 2^32 / grid^2, see band_of)
     int cols;                 // input length (multiple of 32)
     int rows;                 // valid output rows (<= 16 * n_rg / unit_rg for SWIGLU, <= 16 * n_rg otherwise)
     int epi;                  // TEPI_*
@@ -102,8 +103,10 @@ struct TileArgs {
     int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier (single GPU only)
     MegaAttn at;
     float eps;
+    unsigned int g_magic;     // ceil(2^32 / grid), filled in by launch_tiled
     int poll_ns;              // back-off between two looks at a polled phase input (0 = look again at once)
     int att_chunk;            // attention: positions per split while the splits last (<= 96 = one pass)
+    int att_hpi;              // attention: q heads per item; 0 = as few as still give every item its own CTA, >= group = the whole GQA group
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
     unsigned long long *trace2; // optional: [cta][phase][16] clock64 stamps (tools/trace_fine.py)

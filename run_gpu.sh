@@ -1,5 +1,6 @@
-V=nanollama_b200/build/variants
-timeout 500 python tools/decode_ab.py --tier big --layers 10 --timeout 100 --variants "NL_LIB=$V/lib_xb1.so;NL_LIB=$V/lib_cur.so;NL_LIB=$V/lib_cur.so,NL_ATT_CHUNK=48;NL_LIB=$V/lib_cur.so,NL_TILE_POLL=0" 2>&1 | tee gpurun_out/ab4.log
-NL_LIB=$V/lib_tr.so timeout 200 python tools/decode_ab.py --tier big --layers 10 --timeout 100 --steps 64 --reps 1 --trace gpurun_out/tr --variants "NL_TILE_POLL=1" > gpurun_out/ab_trace.log 2>&1
-python tools/trace_summary.py gpurun_out/tr/trace_0.bin > gpurun_out/trace_poll2.md 2>/dev/null; grep "^|\|grid" gpurun_out/trace_poll2.md
-python tools/trace_fine.py gpurun_out/tr/trace_0.bin.ck > gpurun_out/trace_fine_poll2.md 2>&1; cat gpurun_out/trace_fine_poll2.md
+timeout 900 python -m pytest tests -m gpu -q --timeout 600 > gpurun_out/pytest_gpu.log 2>&1; echo "pytest rc=$?"; tail -3 gpurun_out/pytest_gpu.log
+timeout 120 python -c "import __graft_entry__ as g; g.smoke()" 2>&1 | tail -1
+timeout 900 python bench.py > gpurun_out/bench_big.json 2> gpurun_out/bench_big.err; echo "bench rc=$?"; cut -c1-200 gpurun_out/bench_big.json
+timeout 300 python bench.py --impl reference --steps 1 --warmup 0 2>/dev/null | tail -1 | cut -c1-200
+timeout 600 ncu --set full --clock-control none --import-source on -k regex:decode_tiled -s 20 -c 1 -o gpurun_out/prof_tiled python bench.py --steps 1 --warmup 1 --tokens-per-step 32 --no-cpu-baseline > gpurun_out/ncu_tiled.log 2>&1; echo "ncu full rc=$?"
+timeout 400 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:"decode_tiled|embed_kernel|argmax|bump_epoch|feed_prompt" -c 300 --csv --log-file gpurun_out/launches_big_decode.csv python bench.py --steps 1 --warmup 1 --tokens-per-step 32 --no-cpu-baseline > gpurun_out/ncu_big.log 2>&1; echo "ncu list rc=$?"

@@ -359,6 +359,19 @@ def test_long_context_attention_vs_oracle():
     m.close(); o.close()
 
 
+@pytest.mark.parametrize("env", [{"NL_TILE_POLL": "0"}, {"NL_TILE_POLL": "1", "NL_ATT_CHUNK": "48"}, {"NL_ATT_HPI": "1"}, {"NL_ATT_HPI": "99"}],
+                         ids=["barriers", "polled_chunk48", "one_head_per_item", "whole_group_per_item"])
+def test_decode_modes_vs_oracle(env):
+    """The persistent kernel's switches, each in a fresh process: grid barriers instead of polled activations (the path tensor
+    parallelism runs), a finer attention split, and both extremes of the q-heads-per-item distribution -- logits at positions around
+    the split boundaries and a greedy stream against the oracle (tests/mode_worker.py)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    r = subprocess.run([sys.executable, os.path.join(root, "tests", "mode_worker.py")], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+    assert r.returncode == 0 and "MODE_PARITY_OK" in r.stdout, (r.stdout[-2000:], r.stderr[-2000:])
+
+
 # ---------------------------------------------------------------- tensor parallel (needs >= 2 GPUs on the box)
 def test_tensor_parallel_2gpu_parity():
     import socket

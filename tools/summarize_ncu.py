@@ -40,7 +40,8 @@ WANT = ["gpu__time_duration.sum", "dram__bytes_read.sum", "dram__bytes_write.sum
         "launch__registers_per_thread", "launch__grid_size", "launch__block_size", "smsp__inst_executed.sum",
         "smsp__pcsamp_warps_issue_stalled_barrier", "smsp__pcsamp_warps_issue_stalled_long_scoreboard", "smsp__pcsamp_warps_issue_stalled_short_scoreboard",
         "smsp__pcsamp_warps_issue_stalled_math_pipe_throttle", "smsp__pcsamp_warps_issue_stalled_wait", "smsp__pcsamp_warps_issue_stalled_not_selected",
-        "smsp__pcsamp_warps_issue_stalled_mio_throttle"]
+        "smsp__pcsamp_warps_issue_stalled_mio_throttle", "smsp__pcsamp_warps_issue_stalled_membar", "smsp__inst_executed_op_local_ld.sum",
+        "smsp__inst_executed_op_local_st.sum", "l1tex__t_sector_hit_rate.pct", "lts__t_sector_hit_rate.pct"]
 
 
 def full(src, dst):
