@@ -271,8 +271,9 @@ struct nl_model {
     // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
     bool tile_ok = false; int tile_type = NL_Q4_0;
     std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
-    // flagged {value, flag} activation vectors of the tiled path: residual stream, q | k | v, attention output, SwiGLU output
-    uint2 *x_ll = nullptr, *qkv_ll = nullptr, *ao_ll = nullptr, *hb_ll = nullptr;
+    // shared activation vectors of the tiled path's barrier mode (NL_TILE_POLL=0, tensor parallel): residual stream (tensor parallel:
+    // the two exchange residuals), q | k | v, attention output, SwiGLU output
+    uint2 *x_sh = nullptr, *qkv_sh = nullptr, *ao_sh = nullptr, *hb_sh = nullptr;
     float *arena = nullptr; size_t arena_bytes = 0;   // polled single-use activation vectors of the tiled path (nl_tile.cu)
     unsigned int *d_epoch = nullptr;    // launch counter behind the flags
     float2 *amax = nullptr; bool amax_valid = false;   // per-CTA argmax pairs of the LM-head phase
@@ -425,13 +426,13 @@ static int make_tiles(uint8_t **dst, const DevMat *const *mats, int n, bool inte
     }
     return NL_OK;
 }
-// in / out / resid are plain fp32 vectors, or flagged pair vectors when the matching *_ll is set
-static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const void *x, int in_ll,
-                            const float *norm_w, const float *bias, void *out, int out_ll, const void *resid = nullptr, int resid_ll = 0) {
+// in / out / resid are fp32 vectors; *_poll: the vector lives in the single-use arena and is polled for the sentinel (nl_tile.cu)
+static void tile_gemv_phase(TilePhase &P, const uint8_t *tiles, int n_rg, int cols, int unit_rg, int rows, int epi, const void *x, int in_poll,
+                            const float *norm_w, const float *bias, void *out, int out_poll, const void *resid = nullptr, int resid_poll = 0) {
     memset(&P, 0, sizeof P);
     P.kind = PH_GEMV; P.tiles = tiles; P.n_rg = n_rg; P.nbg = (cols / 32 + 3) / 4; P.nbg_magic = tile_magic(P.nbg); P.unit_rg = unit_rg; P.units = n_rg / unit_rg;
     P.cols = cols; P.rows = rows; P.epi = epi; P.x = (const float *)x; P.norm_w = norm_w; P.bias = bias; P.out = (float *)out;
-    P.resid = (const float *)resid; P.in_ll = in_ll; P.out_ll = out_ll; P.resid_ll = resid_ll;
+    P.resid = (const float *)resid; P.in_poll = in_poll; P.out_poll = out_poll; P.resid_poll = resid_poll;
 }
 __global__ void bump_epoch_kernel(unsigned int *epoch) { *epoch += 1; }
 
@@ -458,8 +459,8 @@ static int build_tiled(nl_model *m) {
     if (G > 256 || 5 * c.n_layers + 1 > 1024) return NL_OK;   // window areas of the tensor-parallel exchange
     cudaStream_t st = m->st;
     {
-        struct { uint2 **p; int n; } ll[4] = {{&m->x_ll, dim}, {&m->qkv_ll, nqkv}, {&m->ao_ll, qdim}, {&m->hb_ll, ffn}};
-        for (auto &b : ll) { NL_CUDA(cudaMalloc(b.p, (size_t)b.n * 8)); NL_CUDA(cudaMemset(*b.p, 0, (size_t)b.n * 8)); }
+        struct { uint2 **p; int n; } shv[4] = {{&m->x_sh, dim}, {&m->qkv_sh, nqkv}, {&m->ao_sh, qdim}, {&m->hb_sh, ffn}};
+        for (auto &b : shv) { NL_CUDA(cudaMalloc(b.p, (size_t)b.n * 8)); NL_CUDA(cudaMemset(*b.p, 0, (size_t)b.n * 8)); }
         NL_CUDA(cudaMalloc(&m->d_epoch, 4));
         NL_CUDA(cudaMemset(m->d_epoch, 0, 4));
         NL_CUDA(cudaMalloc(&m->amax, (size_t)G * 8));
@@ -482,9 +483,9 @@ static int build_tiled(nl_model *m) {
     // Single GPU: polled single-use activation vectors, no grid barrier (nl_tile.cu, "polled activations"); per layer
     // q|k|v, attention output, post-attention residual, SwiGLU output, layer output live in one arena that record_forward fills with
     // the sentinel before every launch.  NL_TILE_POLL=0 (and tensor parallel): shared vectors behind release / acquire grid barriers.
-    const int LL = (!tpar && !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0)) ? 1 : 0;
+    const int POLL = (!tpar && !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0)) ? 1 : 0;
     const size_t per_layer = (size_t)nqkv + qdim + dim + ffn + dim;
-    if (LL) {
+    if (POLL) {
         m->arena_bytes = (size_t)c.n_layers * per_layer * 4;
         NL_CUDA(cudaMalloc(&m->arena, m->arena_bytes));
         NL_CUDA(cudaMemset(m->arena, 0xFF, m->arena_bytes));
@@ -493,7 +494,7 @@ static int build_tiled(nl_model *m) {
     // tensor parallel: exchange e (o-projection of layer l: e = 2l, down-projection: e = 2l + 1) uses parity e & 1 of the exchange area;
     // its consumer adds the ranks' partials to the residual before it (the embedding for e = 0, else xres2[(e - 1) & 1]) and leaves
     // the sum in xres2[e & 1]
-    float *xres2[2] = {reinterpret_cast<float *>(m->x_ll), reinterpret_cast<float *>(m->x_ll) + dim};   // 2 x dim floats fit the pair buffer
+    float *xres2[2] = {reinterpret_cast<float *>(m->x_sh), reinterpret_cast<float *>(m->x_sh) + dim};   // 2 x dim floats fit the pair buffer
     auto consume_exchange = [&](TilePhase &Q, int e) {
         Q.in_exch = 1; Q.par = e & 1; Q.prev = e == 0 ? m->x : xres2[(e - 1) & 1]; Q.next = xres2[e & 1];
     };
@@ -510,37 +511,37 @@ static int build_tiled(nl_model *m) {
         if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_dn);
         // this layer's vectors: shared buffers, or (polled) its own slice of the arena; layer 0 reads the embedding kernel's plain x
-        float *a_l = LL ? m->arena + (size_t)l * per_layer : nullptr;
-        void *qkv_l = LL ? (void *)a_l : (void *)m->qkv_ll, *ao_l = LL ? (void *)(a_l + nqkv) : (void *)m->ao_ll;
-        void *hb_l = LL ? (void *)(a_l + nqkv + qdim + dim) : (void *)m->hb_ll;
-        const void *x_in = (l == 0 || !LL) ? (const void *)m->x : (const void *)(a_l - dim);   // the layer before's output
-        if (LL) xres = a_l + nqkv + qdim;            // post-attention residual (output of the o-projection)
-        void *x_out = LL ? (void *)(a_l + nqkv + qdim + dim + ffn) : xres;
-        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, LL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, qkv_l, LL);
+        float *a_l = POLL ? m->arena + (size_t)l * per_layer : nullptr;
+        void *qkv_l = POLL ? (void *)a_l : (void *)m->qkv_sh, *ao_l = POLL ? (void *)(a_l + nqkv) : (void *)m->ao_sh;
+        void *hb_l = POLL ? (void *)(a_l + nqkv + qdim + dim) : (void *)m->hb_sh;
+        const void *x_in = (l == 0 || !POLL) ? (const void *)m->x : (const void *)(a_l - dim);   // the layer before's output
+        if (POLL) xres = a_l + nqkv + qdim;            // post-attention residual (output of the o-projection)
+        void *x_out = POLL ? (void *)(a_l + nqkv + qdim + dim + ffn) : xres;
+        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, POLL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, qkv_l, POLL);
         if (tpar && l > 0) consume_exchange(P, 2 * l - 1);
         ph.push_back(P);
         memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; P.x = (const float *)qkv_l; P.out = (float *)ao_l; ph.push_back(P);
         if (tpar) {
             tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, ao_l, 0, nullptr, ly.bo, nullptr, 0);
             P.exch_out = 1; P.par = 0; P.cross = 1;
-        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, ao_l, LL, nullptr, ly.bo, xres, LL, x_in, LL && l > 0);
+        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, ao_l, POLL, nullptr, ly.bo, xres, POLL, x_in, POLL && l > 0);
         ph.push_back(P);
-        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, LL, ly.ffn_norm, nullptr, hb_l, LL);
+        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, POLL, ly.ffn_norm, nullptr, hb_l, POLL);
         if (tpar) consume_exchange(P, 2 * l);
         ph.push_back(P);
         if (tpar) {
             tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, hb_l, 0, nullptr, nullptr, nullptr, 0);
             P.exch_out = 1; P.par = 1; P.cross = 1;
-        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, hb_l, LL, nullptr, nullptr, x_out, LL, xres, LL);
+        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, hb_l, POLL, nullptr, nullptr, x_out, POLL, xres, POLL);
         ph.push_back(P);
-        if (LL) xres = x_out;   // what the next layer (or the LM head) reads
+        if (POLL) xres = x_out;   // what the next layer (or the LM head) reads
     }
     {
         uint8_t *t_lm = nullptr;
         const DevMat *lm[1] = {&outw};
         if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
         m->tile_bufs.push_back(t_lm);
-        tile_gemv_phase(P, t_lm, lvocab / 16, dim, 1, lvocab, TEPI_STORE, xres, LL, m->output_norm, nullptr, m->logits, 0);
+        tile_gemv_phase(P, t_lm, lvocab / 16, dim, 1, lvocab, TEPI_STORE, xres, POLL, m->output_norm, nullptr, m->logits, 0);
         if (tpar) { consume_exchange(P, 2 * c.n_layers - 1); P.cross = 1; }   // vocab shard -> every rank's full logits vector
         ph.push_back(P);
     }
@@ -559,10 +560,10 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)m->nH * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = LL;
+    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = POLL;
     a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.att_hpi = tile_env_int("NL_ATT_HPI", 0, 0, 64); a.amax = m->amax; m->amax_valid = true;
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
-    a.at.q = reinterpret_cast<float *>(m->qkv_ll); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
+    a.at.q = reinterpret_cast<float *>(m->qkv_sh); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
     a.at.n_heads = m->nH; a.at.n_kv_heads = m->nKV; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
     if (tpar) {   // barrier counters, exchange area, logits and argmax pairs live in the IPC window every peer can write
@@ -570,7 +571,7 @@ static int build_tiled(nl_model *m) {
         a.ar_off = m->tp_lay.ar_data; a.bar_off = m->tp_lay.tile_bar; a.lg_off = m->tp_lay.lg_data; a.amax_off = m->tp_lay.tile_amax;
         a.bar = reinterpret_cast<unsigned int *>(m->tp_win + m->tp_lay.tile_bar);
     }
-    a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_ll); a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
+    a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_sh); a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
     a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
         NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
@@ -995,7 +996,7 @@ void nl_destroy(nl_model *m) {
     if (m->d_trace2) cudaFree(m->d_trace2);
     if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
-    for (void *q : {(void *)m->x_ll, (void *)m->qkv_ll, (void *)m->ao_ll, (void *)m->hb_ll, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
+    for (void *q : {(void *)m->x_sh, (void *)m->qkv_sh, (void *)m->ao_sh, (void *)m->hb_sh, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
     if (m->d_tphases) cudaFree(m->d_tphases);
     if (m->d_phases) cudaFree(m->d_phases);

@@ -90,14 +90,6 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
 #define CK_AT(k) do { } while (0)
 #endif
 // build-time variants of the register allocation around the streaming loop (tools/build_variants.py A/Bs them)
-#ifndef NL_TL_FRAGS_INLINE
-#define NL_TL_FRAGS_INLINE 0
-#endif
-#if NL_TL_FRAGS_INLINE
-#define TL_FRAGS_CALL __forceinline__
-#else
-#define TL_FRAGS_CALL __noinline__
-#endif
 #ifndef NL_TL_STREAM_INLINE
 #define NL_TL_STREAM_INLINE 1
 #endif
@@ -627,7 +619,7 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
     // tile_dot; the RMSNorm scale (one scalar per vector) is applied by the finishing warp to the finished sums:
     // W . (inv * (x o w)) = inv * (W . (x o w)).  The float64 sum of squares is therefore off the critical path.
     double ss = 0.0;
-    constexpr bool in_ll = mode == 1, in_exch = mode == 2;
+    constexpr bool in_poll = mode == 1, in_exch = mode == 2;
     const bool normed = pnw != nullptr;
     float wv0[8];   // norm weights of my first item (items beyond the first only exist for dim > 4096: fetched where they are used)
 #pragma unroll
@@ -659,7 +651,7 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
                     reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
                     reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
                 }
-            } else if (in_ll) {   // look again until none of my 8 elements reads as the sentinel
+            } else if (in_poll) {   // look again until none of my 8 elements reads as the sentinel
                 unsigned int xc[8];
                 ld_item(px, q, xc);
                 while (item_has_sent(xc)) {
@@ -765,9 +757,9 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
 #endif
     double ss;
     if (in_exch) ss = input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
-    else if (P.in_ll) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    else if (P.in_poll) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
     else ss = input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
-    if (trrow && ckrow && P.in_ll) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
+    if (trrow && ckrow && P.in_poll) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[3] = (unsigned long long)clock64();
     if (tid == TL_CONSUMERS - 32 && sh.trace2) sh.trace2[((size_t)blockIdx.x * sh.n_phases + p) * 16 + 6] = (unsigned long long)clock64();
@@ -858,7 +850,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
             const float *resid_src = ldg_ptr(&P->resid);
-            const int out_ll = __ldg(&P->out_ll), resid_ll = __ldg(&P->resid_ll);   // polled vectors (see st_poll)
+            const int out_poll = __ldg(&P->out_poll), resid_poll = __ldg(&P->resid_poll);   // polled vectors (see st_poll)
             const int exch_out = __ldg(&P->exch_out), par = __ldg(&P->par), cross = __ldg(&P->cross);
             const bool to_peers_logits = A.tp > 1 && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
@@ -881,7 +873,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 int q_done = -1;
                 if (epi == TEPI_RESID && c0 > 0 && !exch_out) {
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
-                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_ll ? ld_poll(resid_src, r) : __ldcg(resid_src + r); }
+                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r); }
                 }
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
                 if (lane == 0 && c1 == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
@@ -919,7 +911,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                             else {
                                 const int r = (rg >> 1) * 16 + row;
                                 if (half == 0 && r < rows) {                                   // SiLU(gate)*up, go/model.go:604-606
-                                    if (out_ll) st_poll(out, r, silu_f(gate) * v); else out[r] = silu_f(gate) * v;
+                                    if (out_poll) st_poll(out, r, silu_f(gate) * v); else out[r] = silu_f(gate) * v;
                                 }
                             }
                         } else {
@@ -932,8 +924,8 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                                 } else if (to_peers_logits) {   // vocab-split LM head: my rows of the full logits vector on every rank
                                     for (int rr = 0; rr < A.tp; rr++) reinterpret_cast<float *>(A.peers.win[rr] + A.lg_off)[(size_t)A.rank * A.lvocab + r] = v;
                                 } else {
-                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_ll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
-                                    if (out_ll) st_poll(out, r, v); else out[r] = v;
+                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                    if (out_poll) st_poll(out, r, v); else out[r] = v;
                                 }
                                 const int gr = A.tp > 1 ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
                                 if (v > best || (v == best && gr < best_i)) { best = v; best_i = gr; }   // first maximum, go/main.go:400-408
@@ -1020,7 +1012,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 
         // ---- prologue: phase input -> fp16 hi/lo B fragments in shared memory ----
         if (tid == 0) TL_CK(p, 0);
-        if (P.in_ll && tid == 0) TL_TRACE(p, 0);
+        if (P.in_poll && tid == 0) TL_TRACE(p, 0);
         if (p > 0) {
             if (!poll && tid == 0) { TL_TRACE(p, 0); tl_wait(A, p - 1, P.wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
             // also: every math warp is done with the previous phase's fragments (a polled element can be complete while a slower warp of

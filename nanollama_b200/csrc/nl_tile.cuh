@@ -21,10 +21,14 @@
 //
 // Kernel structure (one CTA per SM, cooperative): 16 math warps + 1 copy warp + 1 finishing warp walk the phase list
 //     per layer: QKV (RMSNorm fused) | attention | O (+residual) | gate/up (RMSNorm fused, SiLU*up) | down (+residual);  LM head
-// separated by grid barriers (one counter per phase).  The copy warp never waits for a barrier (weights do not depend on
-// activations), so the ring keeps HBM busy across phase boundaries.  Per ring slot (32 tiles) each math warp owns two tiles and
-// drops per-row partial sums into shared memory; the finishing warp adds them in a fixed order (deterministic), keeps the
-// running sum of a row group across slots, applies bias / residual / SiLU*up and publishes the outputs.
+// Phase boundaries: on one GPU every activation vector of a token is written once into a sentinel-filled arena and the consumers
+// poll the data itself (no grid barrier, no fence; "polled activations" in nl_tile.cu); under tensor parallelism (and with
+// NL_TILE_POLL=0) release / acquire grid barriers, one counter per phase.  The copy warp never waits for a phase boundary
+// (weights do not depend on activations), so the ring keeps HBM busy across them.  Per ring slot (32 tiles) each math warp owns
+// two tiles and drops per-row partial sums into shared memory; the finishing warp adds them in a fixed order (deterministic),
+// keeps the running sum of a row group across slots, applies bias / residual / SiLU*up and publishes the outputs.
+// Shared memory is 217 KB of the SM's 228, so ~12 KB of L1 remain: whatever ptxas spills goes to L2.  Hence one out-of-line
+// function per phase kind, one set of B fragments in the streaming loop, descriptors read from shared memory where they are used.
 #pragma once
 #include <stdlib.h>
 
@@ -72,12 +76,12 @@ struct TilePhase {
     int cols;                 // input length (multiple of 32)
     int rows;                 // valid output rows (<= 16 * n_rg / unit_rg for SWIGLU, <= 16 * n_rg otherwise)
     int epi;                  // TEPI_*
-    const float *x;           // input vector [cols], fp32 (PH_ATTN: this layer's q | k | v vector); polled for the sentinel when in_ll
+    const float *x;           // input vector [cols], fp32 (PH_ATTN: this layer's q | k | v vector); polled for the sentinel when in_poll
     const float *norm_w;      // non-null: input is RMSNorm(x; norm_w), go/quant.go:597-607
     const float *bias;        // optional [rows]
-    float *out;               // output vector (PH_ATTN: the attention output); stored with st_poll when out_ll
-    const float *resid;       // TEPI_RESID: the vector the product is added to (polled when resid_ll)
-    int in_ll, out_ll, resid_ll;   // TileArgs::poll: the vector lives in the single-use arena (see "polled activations" in nl_tile.cu)
+    float *out;               // output vector (PH_ATTN: the attention output); stored with st_poll when out_poll
+    const float *resid;       // TEPI_RESID: the vector the product is added to (polled when resid_poll)
+    int in_poll, out_poll, resid_poll;   // TileArgs::poll: the vector lives in the single-use arena (see "polled activations" in nl_tile.cu)
     // ---- tensor parallel (TileArgs::tp > 1) ----
     int exch_out;             // row-split matrix (O / down): the product is this rank's PARTIAL; it is stored into slot `rank` of
                               // parity `par` of every peer's exchange area instead of being added to the residual

@@ -2,8 +2,8 @@
 """Build-time variants of the tiled decode kernel for A/B runs: nl_tile.cu is recompiled with the given -D flags and linked with the
 regular objects into nanollama_b200/build/variants/lib_<name>.so; NL_LIB=<path> makes nanollama_b200.capi load that library.
 
-    python tools/build_variants.py base: inl:-DNL_TL_FRAGS_INLINE=1 xb1:-DNL_TL_XB_SINGLE=1
-    python tools/decode_ab.py --variants "NL_LIB=nanollama_b200/build/variants/lib_base.so;NL_LIB=nanollama_b200/build/variants/lib_xb1.so"
+    python tools/build_variants.py base: xb2:-DNL_TL_XB_SINGLE=0 tr:-DNL_TL_FINE_TRACE=1
+    python tools/decode_ab.py --variants "NL_LIB=nanollama_b200/build/variants/lib_base.so;NL_LIB=nanollama_b200/build/variants/lib_xb2.so"
 """
 import os
 import re
