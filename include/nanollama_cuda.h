@@ -107,6 +107,14 @@ int nl_get_logits(nl_model *m, float *logits_out);
 int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int32_t n_new, int32_t eos_id,
                        int32_t *out_tokens, int32_t *n_out);
 
+/* ---- one sampling step of Engine.Generate (go/main.go:177-197, :294-398) on the logits the last nl_forward left on the device,
+ * so that they never cross PCIe and the host does not sort the vocabulary: repetition penalty over `recent` (n_recent tokens, once
+ * per occurrence, applied in place like the reference does to State.Logits), then sampleTopP when top_p < 1, else sampleTopK;
+ * temperature <= 0: argmax.  u = the uniform number rng.Float32() the reference would draw at this step (drawn by the host, so the
+ * random stream stays the host's; ignored when temperature <= 0).  *token_out = the sampled token id. ---- */
+int nl_sample(nl_model *m, float temperature, int32_t top_k, float top_p, float rep_penalty, const int32_t *recent, int32_t n_recent,
+              float u, int32_t *token_out);
+
 /* ---- B independent sequences, one token each (small-batch decode; same weights, per-sequence KV cache).
  * tokens/pos: B int32 each; logits_out: [B, vocab_size] host floats or NULL.  B <= max_batch. ---- */
 int nl_forward_batch(nl_model *m, int32_t B, const int32_t *tokens, const int32_t *pos, float *logits_out);

@@ -48,6 +48,7 @@ SIGNATURES = {
     "nl_reset": (C.c_int, [_vp]),
     "nl_get_logits": (C.c_int, [_vp, _vp]),
     "nl_generate_greedy": (C.c_int, [_vp, _vp, _i32, _i32, _i32, _vp, C.POINTER(_i32)]),
+    "nl_sample": (C.c_int, [_vp, C.c_float, _i32, C.c_float, C.c_float, _vp, _i32, C.c_float, C.POINTER(_i32)]),
     "nl_forward_batch": (C.c_int, [_vp, _i32, _vp, _vp, _vp]),
     "nl_prefill": (C.c_int, [_vp, _vp, _i32, _i32, _vp]),
     "nl_dequant": (C.c_int, [_u32, _vp, _i64, _vp]),

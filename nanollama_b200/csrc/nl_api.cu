@@ -14,6 +14,7 @@
 #include "nl_stream.cuh"
 #include "nl_mega.cuh"
 #include "nl_tile.cuh"
+#include "nl_sample.cuh"
 #include <string>
 #include "nl_tp.cuh"
 #include "nl_gemm.cuh"
@@ -248,6 +249,9 @@ struct nl_model {
     int gen_cap = 0, prompt_cap = 0;
     int32_t *h_stage = nullptr;  // pinned: tokens[B], pos[B]
     float *h_logits = nullptr;   // pinned [B][vocab]
+    // device-side sampling (nl_sample.cu): sort scratch, repetition window, result; allocated on first use
+    uint32_t *sp_keys = nullptr; int32_t *sp_idx = nullptr, *sp_recent = nullptr, *sp_token = nullptr; int32_t *sp_host = nullptr;
+    static constexpr int SP_RECENT_CAP = 4096;
     bool finalized = false;
     std::vector<cudaGraphExec_t> g_fwd, g_step;  // index = batch
     int launches_fwd = 0;
@@ -1005,6 +1009,8 @@ void nl_destroy(nl_model *m) {
     if (m->part_ml) cudaFree(m->part_ml);
     if (m->h_stage) cudaFreeHost(m->h_stage);
     if (m->h_logits) cudaFreeHost(m->h_logits);
+    if (m->sp_host) cudaFreeHost(m->sp_host);
+    for (void *q : {(void *)m->sp_keys, (void *)m->sp_idx, (void *)m->sp_recent, (void *)m->sp_token}) if (q) cudaFree(q);
     if (m->ev0) cudaEventDestroy(m->ev0);
     if (m->ev1) cudaEventDestroy(m->ev1);
     if (m->st) cudaStreamDestroy(m->st);
@@ -1046,6 +1052,37 @@ int nl_get_logits(nl_model *m, float *logits_out) {
     NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));
     memcpy(logits_out, m->h_logits, (size_t)m->c.vocab_size * 4);
+    return NL_OK;
+}
+
+// One sampling step of Engine.Generate on the logits the last forward left on the device (go/main.go:177-197, :294-398).
+int nl_sample(nl_model *m, float temperature, int32_t top_k, float top_p, float rep_penalty, const int32_t *recent, int32_t n_recent, float u,
+              int32_t *token_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (!token_out || n_recent < 0 || (n_recent > 0 && !recent)) return fail(NL_ERR_INVALID, "bad argument");
+    if (n_recent > nl_model::SP_RECENT_CAP) return fail(NL_ERR_INVALID, "repetition window of %d tokens exceeds %d", n_recent, nl_model::SP_RECENT_CAP);
+    if (temperature > 0.f && !(top_p < 1.0f) && top_k < 1) return fail(NL_ERR_INVALID, "top_k must be >= 1");
+    if (!(u >= 0.f && u < 1.f)) return fail(NL_ERR_INVALID, "u must be in [0, 1)");
+    const int vocab = m->c.vocab_size;
+    if (!m->sp_keys) {
+        NL_CUDA(cudaMalloc(&m->sp_keys, (size_t)vocab * 2 * sizeof(uint32_t)));
+        NL_CUDA(cudaMalloc(&m->sp_idx, (size_t)vocab * 2 * sizeof(int32_t)));
+        NL_CUDA(cudaMalloc(&m->sp_recent, (size_t)nl_model::SP_RECENT_CAP * sizeof(int32_t)));
+        NL_CUDA(cudaMalloc(&m->sp_token, sizeof(int32_t)));
+        NL_CUDA(cudaMallocHost(&m->sp_host, (size_t)(nl_model::SP_RECENT_CAP + 1) * sizeof(int32_t)));
+    }
+    if (n_recent > 0) {
+        memcpy(m->sp_host + 1, recent, (size_t)n_recent * sizeof(int32_t));   // pinned staging: `recent` is caller memory
+        NL_CUDA(cudaMemcpyAsync(m->sp_recent, m->sp_host + 1, (size_t)n_recent * sizeof(int32_t), cudaMemcpyHostToDevice, m->st));
+    }
+    SampleArgs a;
+    a.logits = m->logits; a.vocab = vocab; a.recent = m->sp_recent; a.n_recent = n_recent; a.rep_penalty = rep_penalty;
+    a.temp = temperature; a.top_k = top_k; a.top_p = top_p; a.u = u;
+    a.keys0 = m->sp_keys; a.keys1 = m->sp_keys + vocab; a.idx0 = m->sp_idx; a.idx1 = m->sp_idx + vocab; a.token_out = m->sp_token;
+    if (launch_sample(a, m->st)) return fail(NL_ERR_CUDA, "sample kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    NL_CUDA(cudaMemcpyAsync(m->sp_host, m->sp_token, sizeof(int32_t), cudaMemcpyDeviceToHost, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    *token_out = m->sp_host[0];
     return NL_OK;
 }
 

@@ -32,7 +32,10 @@ class Engine:
     """go/main.go:143-149."""
 
     def __init__(self, model, eos_id: int = 2, rep_penalty: float = 1.15, rep_window: int = 64, seed: Optional[int] = None,
-                 decode_token: Optional[Callable[[int], str]] = None):
+                 decode_token: Optional[Callable[[int], str]] = None, device_sampling: bool = False):
+        # device_sampling: repetition penalty + sampleTopK / sampleTopP run on the device (nl_sample) on logits that never leave HBM;
+        # the random numbers are still drawn here, one per sampled token, exactly where the host samplers draw theirs
+        self.device_sampling = bool(device_sampling)
         self.model = model
         self.eos_id = eos_id
         self.rep_penalty = float(rep_penalty)
@@ -92,10 +95,12 @@ class Engine:
     def generate_tokens(self, prompt_tokens: Sequence[int], p: GenParams, on_token: Optional[Callable[[int], None]] = None) -> List[int]:
         m = self.model
         seq_len = m.config.seq_len
+        dev = self.device_sampling
+        fwd = m.forward_device if dev else m.forward
         m.reset()
         pos = 0
         for tok in prompt_tokens:
-            m.forward(int(tok), pos)
+            fwd(int(tok), pos)
             pos += 1
             if pos >= seq_len - 1:
                 break
@@ -105,6 +110,26 @@ class Engine:
         for _ in range(p.max_tokens):
             if out_bytes >= 8192:
                 break
+            if dev:
+                # the host samplers draw one rng.Float32() per sampled token, and none when temperature <= 0 (main.go:299, :351)
+                u = float(np.float32(self.rng.random())) if p.temperature > 0 else 0.0
+                if u >= 1.0:
+                    u = float(np.nextafter(np.float32(1.0), np.float32(0.0)))
+                nxt = m.sample(p.temperature, p.top_k, p.top_p, self.rep_penalty, recent, u)
+                recent.append(nxt)
+                if len(recent) > self.rep_window:
+                    recent = recent[1:]
+                if nxt == self.eos_id:
+                    break
+                out.append(nxt)
+                out_bytes += len(self.decode_token(nxt).encode("utf-8"))
+                if on_token:
+                    on_token(nxt)
+                fwd(nxt, pos)
+                pos += 1
+                if pos >= seq_len:
+                    break
+                continue
             logits = m.state.logits
             if self.rep_penalty > 1.0 and recent:  # go/main.go:177-187 — in place, also when temp == 0
                 for tok in recent:

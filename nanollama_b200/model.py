@@ -67,6 +67,28 @@ class LlamaModel:
             raise IndexError(capi.lib().nl_last_error().decode())
         capi.check(rc)
 
+    def forward_device(self, token: int, pos: int) -> None:
+        """Forward whose logits stay on the device (nl_forward with logits_out = NULL): the companion of ``sample``."""
+        rc = capi.lib().nl_forward(self._h, int(token), int(pos), None)
+        if rc == capi.NL_ERR_INVALID:
+            raise IndexError(capi.lib().nl_last_error().decode())
+        capi.check(rc)
+
+    def sample(self, temperature: float, top_k: int, top_p: float, rep_penalty: float, recent: Sequence[int], u: float) -> int:
+        """One sampling step of Engine.Generate on the device-resident logits (go/main.go:177-197, :294-398): nl_sample.
+        ``u`` is the uniform number the reference's rng.Float32() would deliver at this step."""
+        r = np.ascontiguousarray(recent, dtype=np.int32)
+        tok = C.c_int32(0)
+        rc = capi.lib().nl_sample(self._h, float(temperature), int(top_k), float(top_p), float(rep_penalty), capi.ptr(r) if r.size else None, int(r.size),
+                                  float(u), C.byref(tok))
+        capi.check(rc)
+        return int(tok.value)
+
+    def get_logits(self) -> np.ndarray:
+        """State.Logits read-back of the device-resident logits (nl_get_logits)."""
+        capi.check(capi.lib().nl_get_logits(self._h, capi.ptr(self.state.logits)))
+        return self.state.logits
+
     def reset(self) -> None:
         capi.check(capi.lib().nl_reset(self._h))
         self.state.pos = 0

@@ -1,2 +1,1 @@
-for c in "mini q4_0" "mini q8_0" "goldie q4_0"; do set -- $c; timeout 200 python bench.py --tier $1 --dtype $2 --steps 5 --warmup 3 --no-cpu-baseline 2>/dev/null | tail -1 > gpurun_out/bench_$1_$2.json; python -c "
-import json,sys; d=json.load(open('gpurun_out/bench_$1_$2.json')); print('$1 $2', round(d['value'],1), 'tok/s frac', round(d['roofline']['frac'],3), 'e2e', round(d['e2e']['value'],1), d['config'].get('decode_path',''))"; done
+timeout 300 python -m pytest tests/test_gpu_parity.py -m gpu -q -x --timeout 200 -k "sampling" 2>&1 | tail -15

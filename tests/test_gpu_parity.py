@@ -442,3 +442,79 @@ def test_prefill_mini_tier_512_tokens():
     m.reset(); m.prefill(toks)
     assert np.array_equal(a, m.state.logits) and np.isfinite(a).all()
     m.close()
+
+
+# ---------------------------------------------------------------- device-side sampling (nl_sample; go/main.go:177-197, :294-398)
+class _FixedRng:
+    def __init__(self, u):
+        self.u = u
+
+    def random(self):
+        return self.u
+
+
+def _sampling_model():
+    gf = T.SyntheticGGUF("mini", G.GGML_Q4_0, seed=5, seq_len=96, vocab=4096, layers=2)
+    m = M.load_llama_model(gf)
+    for pos, t in enumerate([1, 77, 1234, 9]):
+        m.forward(t, pos)
+    return m
+
+
+def test_device_sampling_matches_host_samplers():
+    """nl_sample on the device-resident logits against the host mirror of sampleTopK / sampleTopP (engine.py, itself a restatement of
+    go/main.go:294-398) for the same uniform random number: same token (a disagreement needs the random number within an ulp of a cdf
+    step, so at most one is tolerated over the sweep)."""
+    from nanollama_b200.engine import Engine
+    m = _sampling_model()
+    host = Engine(m, seed=0)
+    logits = m.state.logits.copy()
+    bad, total = [], 0
+    for temp, top_k, top_p in [(0.8, 50, 0.9), (1.0, 40, 1.0), (0.7, 5, 1.0), (1.3, 3000, 1.0), (0.9, 50, 0.5), (2.5, 50, 0.99), (0.0, 50, 0.9)]:
+        for u in (0.0, 0.013, 0.25, 0.5, 0.77, 0.9991):
+            m.state.logits[:] = logits
+            host.rng = _FixedRng(u)
+            exp = host.sample_top_p(temp, top_p) if top_p < 1.0 else host.sample_top_k(temp, top_k)
+            got = m.sample(temp, top_k, top_p, 1.0, [], float(np.float32(u)))
+            total += 1
+            if got != exp:
+                bad.append((temp, top_k, top_p, u, exp, got))
+    assert len(bad) <= 1, (bad[:5], total)
+    # the logits were not touched (no repetition penalty asked for)
+    assert np.array_equal(m.get_logits(), logits)
+    m.close()
+
+
+def test_device_sampling_repetition_penalty_in_place():
+    """The penalty is applied to the device logits in place, once per occurrence in the window (go/main.go:177-187), then argmax."""
+    m = _sampling_model()
+    logits = m.state.logits.copy()
+    top = int(np.argmax(logits))
+    neg = int(np.argmin(logits))
+    recent = [top, neg, top, 4095, top]
+    pen = np.float32(1.3)
+    exp = logits.copy()
+    for t in recent:
+        exp[t] = np.float32(exp[t] / pen) if exp[t] > 0 else np.float32(exp[t] * pen)
+    got_tok = m.sample(0.0, 50, 0.9, float(pen), recent, 0.0)
+    assert np.array_equal(m.get_logits(), exp)
+    assert got_tok == int(np.argmax(exp))
+    with pytest.raises(Exception):
+        m.sample(0.8, 0, 1.0, 1.0, [], 0.5)       # top_k < 1 with top-k sampling
+    with pytest.raises(Exception):
+        m.sample(0.8, 50, 0.9, 1.0, [], 1.0)      # u outside [0, 1)
+    m.close()
+
+
+@pytest.mark.parametrize("top_p,top_k", [(0.9, 50), (1.0, 40)])
+def test_engine_device_sampling_same_stream_as_host_sampling(top_p, top_k):
+    """Engine.generate_tokens with the samplers on the device (logits never leave HBM) against the host samplers, same seed: the
+    same tokens (the default repetition penalty 1.15 over a 64-token window included)."""
+    from nanollama_b200.engine import Engine, GenParams
+    m = _sampling_model()
+    p = GenParams(max_tokens=40, temperature=0.8, top_p=top_p, top_k=top_k)
+    prompt = [1, 5, 99, 1000]
+    a = Engine(m, eos_id=-1, seed=123).generate_tokens(prompt, p)
+    b = Engine(m, eos_id=-1, seed=123, device_sampling=True).generate_tokens(prompt, p)
+    assert len(a) == 40 and a == b, (a, b)
+    m.close()
