@@ -171,6 +171,35 @@ func (m *LlamaModel) GenerateGreedyCUDA(prompt []int, maxTokens, eosID int) ([]i
 	return res, nil
 }
 
+// ForwardDeviceCUDA is Forward with the logits left on the device (State.Logits is not refreshed): the companion of SampleCUDA.
+func (m *LlamaModel) ForwardDeviceCUDA(token, pos int) {
+	if rc := C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), nil); rc != 0 {
+		panic(nlErr(rc, "forward"))
+	}
+	m.State.Pos = pos + 1
+}
+
+// SampleCUDA is one sampling step of Engine.Generate (main.go:177-197: repetition penalty over recentTokens, then
+// sampleTopP when topP < 1 else sampleTopK, argmax when temp <= 0) on the device-resident logits of the last forward.
+// u must be the e.rng.Float32() the host samplers would draw at this step (drawn only when temp > 0), so that a seeded
+// run produces the reference's token stream.
+func (m *LlamaModel) SampleCUDA(temp float32, topK int, topP, repPenalty float32, recentTokens []int, u float32) (int, error) {
+	var rp *C.int32_t
+	rec := make([]C.int32_t, len(recentTokens))
+	for i, t := range recentTokens {
+		rec[i] = C.int32_t(t)
+	}
+	if len(rec) > 0 {
+		rp = &rec[0]
+	}
+	var tok C.int32_t
+	rc := C.nl_sample(m.cuda.h, C.float(temp), C.int32_t(topK), C.float(topP), C.float(repPenalty), rp, C.int32_t(len(rec)), C.float(u), &tok)
+	if err := nlErr(rc, "sample"); err != nil {
+		return 0, err
+	}
+	return int(tok), nil
+}
+
 // Close releases the device memory (there is no counterpart in the reference: its weights are Go slices).
 // DecodePath names the kernel family that runs a batch-1 Forward of this model ("decode_tiled_kernel", ...): for the banner / logs.
 func (m *LlamaModel) DecodePath() string { return C.GoString(C.nl_decode_path(m.cuda.h)) }
