@@ -173,10 +173,9 @@ func (m *LlamaModel) GenerateGreedyCUDA(prompt []int, maxTokens, eosID int) ([]i
 
 // ForwardDeviceCUDA is Forward with the logits left on the device (State.Logits is not refreshed): the companion of SampleCUDA.
 func (m *LlamaModel) ForwardDeviceCUDA(token, pos int) {
-	if rc := C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), nil); rc != 0 {
-		panic(nlErr(rc, "forward"))
+	if rc := C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), nil); rc != C.NL_OK {
+		panic(nlErr(rc, "Forward"))
 	}
-	m.State.Pos = pos + 1
 }
 
 // SampleCUDA is one sampling step of Engine.Generate (main.go:177-197: repetition penalty over recentTokens, then
