@@ -85,3 +85,37 @@ def test_argmax_first_maximum():
 
 def test_estimate_params(model):
     assert estimate_params(model.config) == 2 * 256 * 128 + 2 * (128 * 128 + 2 * 128 * 64 + 128 * 128 + 3 * 128 * 512 + 256) + 128
+
+
+class DeviceSamplingStub(OracleAdapter):
+    """The two calls Engine(device_sampling=True) makes, restated on the host: forward_device = Forward without a logits copy,
+    sample = what nl_sample does (penalty in place over the window, then the host samplers fed the given random number)."""
+
+    def forward_device(self, t, p):
+        self.forward(t, p)
+
+    def sample(self, temperature, top_k, top_p, rep_penalty, recent, u):
+        lg = self.state.logits
+        if rep_penalty > 1.0:
+            for tok in recent:
+                if 0 <= tok < self.config.vocab_size:
+                    lg[tok] = np.float32(lg[tok] / np.float32(rep_penalty)) if lg[tok] > 0 else np.float32(lg[tok] * np.float32(rep_penalty))
+        helper = Engine(self, seed=0)
+        helper.rng = SimpleNamespace(random=lambda: u)
+        return helper.sample_top_p(temperature, top_p) if top_p < 1.0 else helper.sample_top_k(temperature, top_k)
+
+
+@pytest.mark.parametrize("params", [GenParams(max_tokens=40, temperature=0.8, top_p=0.9, top_k=50), GenParams(max_tokens=40, temperature=1.1, top_p=1.0, top_k=7),
+                                    GenParams(max_tokens=20, temperature=0.0, top_p=0.9, top_k=50)])
+def test_device_sampling_loop_draws_and_windows_like_the_host_loop(golden_dir, prompt, params):
+    """Engine(device_sampling=True) against the host loop, same seed: one random number per sampled token (none when greedy), the same
+    repetition window, EOS and context-end handling -- so the two produce the same tokens when `sample` is exact."""
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    host = Engine(OracleAdapter(gf), eos_id=-1, rep_penalty=1.15, rep_window=8, seed=11).generate_tokens(prompt, params)
+    dev = Engine(DeviceSamplingStub(gf), eos_id=-1, rep_penalty=1.15, rep_window=8, seed=11, device_sampling=True).generate_tokens(prompt, params)
+    assert host == dev and len(host) == params.max_tokens
+    eos = host[5]
+    k = host.index(eos)
+    host2 = Engine(OracleAdapter(gf), eos_id=eos, rep_penalty=1.15, rep_window=8, seed=11).generate_tokens(prompt, params)
+    dev2 = Engine(DeviceSamplingStub(gf), eos_id=eos, rep_penalty=1.15, rep_window=8, seed=11, device_sampling=True).generate_tokens(prompt, params)
+    assert host2 == dev2 == host[:k]
