@@ -91,7 +91,8 @@ def logits_case(name, n, rng):
 
 @pytest.mark.parametrize("name,n", [("peaked", 32000), ("flat", 5000), ("near_flat", 40000), ("one_hot", 4096), ("ties_and_zeros", 3000), ("peaked", 300)])
 def test_kernel_algorithm_selects_the_reference_token(name, n):
-    rng = np.random.default_rng(hash(name) % 1000 + n)
+    import zlib
+    rng = np.random.default_rng(zlib.crc32(name.encode()) % 1000 + n)
     lg = logits_case(name, n, rng)
     model = SimpleNamespace(state=SimpleNamespace(logits=lg.copy()), config=SimpleNamespace(vocab_size=n))
     host = Engine(model, seed=0)
@@ -101,11 +102,15 @@ def test_kernel_algorithm_selects_the_reference_token(name, n):
             host.rng = SimpleNamespace(random=lambda: u)
             exp = host.sample_top_p(temp, top_p) if top_p < 1.0 else host.sample_top_k(temp, top_k)
             got = kernel_algorithm(lg, temp, top_k, top_p, u, stats)
-            if name == "ties_and_zeros" and got != exp:
-                # -0.0 sorts below +0.0 by key but compares equal in the reference: only the order among equal logits may differ
-                assert lg[got] == lg[exp]
-            else:
-                assert got == exp, (name, temp, top_k, top_p, u)
+            if got != exp:
+                # Only the order among EQUAL entries may differ: -0.0 sorts below +0.0 by key but compares equal in the reference, and
+                # sampleTopP orders by NORMALISED probability, where distinct logits can round to the same fp32 value (the kernel orders
+                # by logit; the reference's sort.Slice is not stable, so the order among equal probabilities is arbitrary there too)
+                assert temp > 0 and name in ("ties_and_zeros", "near_flat"), (name, temp, top_k, top_p, u)
+                w = soft(lg, lg.max(), temp)
+                if top_p < 1.0:
+                    w = (w * (np.float32(1.0) / np.cumsum(w, dtype=np.float32)[-1])).astype(np.float32)
+                assert w[got] == w[exp], (name, temp, top_k, top_p, u)
     if name == "near_flat":
         assert stats[1] > 0   # more tokens share the boundary bin than SP_CAND_MAX: the whole-vocabulary fallback was exercised
     if name == "peaked":
