@@ -11,6 +11,9 @@
 // result): 1024 weights at a time are evaluated in parallel into shared memory, one thread adds them up in order -- including
 // sampleTopP's normalising sum over the whole vocabulary in index order.  The random number is supplied by the host
 // (rng.Float32()), which keeps the stream of random numbers the host's.
+// What can differ from the reference is the order among EQUAL entries only: sampleTopP sorts by normalised probability with an
+// unstable sort (sort.Slice), so tokens whose probabilities round to the same fp32 value come in an arbitrary order there; here they
+// come by logit, then by index (tests/test_sampler_algorithm.py pins this on the CPU).
 #include "nl_sample.cuh"
 
 namespace nl {
