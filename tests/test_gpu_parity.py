@@ -286,6 +286,28 @@ def test_gamma_injection(golden_dir, gold):
     m.close()
 
 
+def test_gamma_npz_written_by_the_reference_end_to_end(golden_dir):
+    """gamma_ref.npz (written by scripts/extract_gamma.py's save_gamma_npz, tests/golden/make_gamma_golden.py) -> the go/gamma.go mirror
+    -> nl_set_gamma: logits of tokens with and without a gamma row against the oracle fed the same dense rows."""
+    from nanollama_b200 import gamma as GM
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    g = GM.load_gamma(os.path.join(golden_dir, "gamma_ref.npz"))
+    assert GM.attach(m, g)
+    o.set_gamma(g.values, g.token_to_row(256))
+    plain = O.OracleModel(gf)
+    changed = 0
+    for pos, t in enumerate([1, 3, 17, 42, 200, 255]):
+        m.forward(int(t), pos)
+        exp = o.forward(int(t), pos)
+        assert maxrel(m.state.logits, exp) < 2e-5
+        changed += int(not np.array_equal(exp, plain.forward(int(t), pos)))
+    assert changed >= 4   # the gamma rows do change the logits
+    assert not GM.attach(m, None)
+    m.close()
+
+
 # ---------------------------------------------------------------- BASELINE.json configs 1 and 2
 @pytest.mark.parametrize("tier,typ,n_new", [("nano", G.GGML_Q8_0, 256), ("mini", G.GGML_Q8_0, 256), ("mini", G.GGML_Q4_0, 256)])
 def test_tier_greedy_256_identical(tier, typ, n_new):
