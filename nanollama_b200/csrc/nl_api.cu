@@ -590,12 +590,16 @@ static int build_tiled(nl_model *m) {
     return NL_OK;
 }
 
+static bool batch_gemm_ok(const nl_model *m, int batch);
+static int record_forward_batch_gemm(nl_model *m, int batch);
+
 // The launch sequence of one Forward for `batch` sequences (go/model.go:490-620).  Recorded into a CUDA graph.
 static int record_forward(nl_model *m, int batch) {
     const nl_config &c = m->c;
     cudaStream_t st = m->st;
     const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = m->ffn;   // shard sizes when tp > 1
     const bool tpar = m->tp > 1;
+    if (batch_gemm_ok(m, batch)) return record_forward_batch_gemm(m, batch);
     int launches = 0;
     {   // 1. embedding (+gamma), model.go:500-507
         dim3 grid((dim + 255) / 256, batch);
@@ -695,6 +699,85 @@ static int record_forward(nl_model *m, int batch) {
     return NL_OK;
 }
 
+// Scratch of the GEMM paths (one-pass prefill, batched decode): activations of up to `rows` token rows as fp32 and as bf16 hi | lo planes.
+static int ensure_pf(nl_model *m) {
+    // sized once for the longest prompt and the largest batch: captured graphs keep these pointers
+    const int rows = m->B > m->c.seq_len ? m->B : m->c.seq_len;
+    if (m->pf_cap >= rows) return NL_OK;
+    if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); m->pf_cap = 0; }
+    const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, ld = qdim + 2 * kvd;
+    const size_t T = (size_t)rows;
+    size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
+    NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4)); NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
+    NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
+    NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
+    m->pf_cap = rows;
+    return NL_OK;
+}
+
+// Batched decode on the tensor cores (NL_BATCH_GEMM=1, not validated on a GPU yet -- see DESIGN section 6): B >= 16 sequences are B token
+// rows of the prefill GEMMs (tcgen05, weights dequantised once per 256 rows) instead of B accumulators of the CUDA-core GEMV, with the
+// per-sequence decode attention in between.  Every kernel on this path already runs in nl_prefill / the batch path.
+static bool batch_gemm_ok(const nl_model *m, int batch) {
+    if (!getenv("NL_BATCH_GEMM") || batch < 16 || m->tp > 1) return false;
+    const DevMat &out = m->output.present() ? m->output : m->tok_embd;
+    if (!gemm_eligible(out)) return false;
+    for (const Layer &ly : m->L)
+        for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown})
+            if (!gemm_eligible(*w)) return false;
+    return true;
+}
+static int record_forward_batch_gemm(nl_model *m, int batch) {
+    const nl_config &c = m->c;
+    cudaStream_t st = m->st;
+    const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = m->ffn, B = batch;
+    int launches = 0, rc;
+    {
+        dim3 grid((dim + 255) / 256, B);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim, 1, m->act_stride);
+        launches++;
+    }
+    for (int l = 0; l < c.n_layers; l++) {
+        Layer &ly = m->L[l];
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        if ((rc = gemm_run(ly.wq, m->pf_hi, m->pf_lo, B, ly.bq, m->q, qdim, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wk, m->pf_hi, m->pf_lo, B, ly.bk, m->k, kvd, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wv, m->pf_hi, m->pf_lo, B, ly.bv, m->v, kvd, GEPI_STORE, st))) return rc;
+        {   // RoPE, QK-norm, KV write, attention per sequence: model.go:530-587
+            AttnArgs a;
+            a.q = m->q; a.k = m->k; a.v = m->v;
+            a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
+            a.seq_stride = (int64_t)c.n_layers * S * kvd;
+            a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.pos = m->d_pos; a.out = m->xb2;
+            a.n_heads = m->nH; a.n_kv_heads = m->nKV; a.seq_len = S; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate;
+            a.eps = c.rms_norm_eps; a.scale = (float)(1.0 / sqrt((double)hd));
+            dim3 grid(m->nH, B);
+            if (hd == 64) attn_decode_kernel<64><<<grid, 128, S * sizeof(float), st>>>(a);
+            else attn_decode_kernel<128><<<grid, 128, S * sizeof(float), st>>>(a);
+        }
+        if ((rc = split_planes(m->xb2, m->pf_hi, m->pf_lo, (int64_t)B * qdim, st))) return rc;
+        if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, B, ly.bo, m->x, dim, GEPI_RESID, st))) return rc;
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        if ((rc = gemm_run(ly.wgate, m->pf_hi, m->pf_lo, B, nullptr, m->pf_g, ffn, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(ly.wup, m->pf_hi, m->pf_lo, B, nullptr, m->pf_u, ffn, GEPI_STORE, st))) return rc;
+        {
+            const int64_t ne = (int64_t)B * ffn;
+            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
+        }
+        if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, B, nullptr, m->x, dim, GEPI_RESID, st))) return rc;
+        launches += 12;
+    }
+    {   // final norm + LM head for every sequence, model.go:616-619
+        const DevMat &out = m->output.present() ? m->output : m->tok_embd;
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, m->output_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        if ((rc = gemm_run(out, m->pf_hi, m->pf_lo, B, nullptr, m->logits, c.vocab_size, GEPI_STORE, st))) return rc;
+        launches += 2;
+    }
+    NL_CUDA(cudaGetLastError());
+    m->launches_fwd = launches;
+    return NL_OK;
+}
+
 static int record_advance(nl_model *m, int batch) {
     StepState s{m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->gen_cap};
     // batch 1 on the tiled path: the LM-head phase of the previous forward left one (max, index) pair per CTA
@@ -711,6 +794,7 @@ static int build_graphs(nl_model *m, int batch) {
     if ((int)m->g_fwd.size() <= batch) { m->g_fwd.resize(batch + 1, nullptr); m->g_step.resize(batch + 1, nullptr); }
     if (m->g_fwd[batch]) return NL_OK;
     cudaGraph_t g;
+    if (batch_gemm_ok(m, batch)) { int rc0 = ensure_pf(m); if (rc0) return rc0; }   // no allocation inside a capture
     NL_CUDA(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
     int rc = record_forward(m, batch);
     cudaError_t e = cudaStreamEndCapture(m->st, &g);
@@ -1121,14 +1205,7 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     const nl_config &c = m->c;
     const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, S = c.seq_len, ld = qdim + 2 * kvd;
     cudaStream_t st = m->st;
-    if (!m->pf_cap) {
-        const size_t T = (size_t)S;
-        size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
-        NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4)); NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
-        NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
-        NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
-        m->pf_cap = S;
-    }
+    { int rc0 = ensure_pf(m); if (rc0) return rc0; }
     NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     NL_CUDA(cudaStreamSynchronize(st));   // tokens is caller memory
     {
