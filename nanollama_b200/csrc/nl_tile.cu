@@ -351,8 +351,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, const float *qk
     const int tid = threadIdx.x;
     const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
     unsigned long long *trace = (sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
-    unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
-    (void)ck;
+    [[maybe_unused]] unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
     constexpr int HD = 64, HALF = 32;
     const int group = I.nh, kvd = at.n_kv_heads * HD;   // "group": the q heads of THIS item (I.h0 .. I.h0 + group - 1)
     const int warp = tid >> 5, lane = tid & 31;
@@ -566,7 +565,7 @@ __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic,
     asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(corr_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
     int B = t0 - rg_of(t0, nbg, magic) * nbg;
     const int stepB = TS - rg_of(TS, nbg, magic) * nbg;
-    int cb0 = -1, cb1 = -1;                // block groups whose fragments xb0 / xb1 hold
+    [[maybe_unused]] int cb0 = -1, cb1 = -1;   // block groups whose fragments xb0 / xb1 hold
 #if NL_TL_XB_SINGLE
 #define cb1 cb0
 #endif
@@ -790,7 +789,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     __shared__ TlShared sh;
     uint8_t *ring = smem;
     uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
-    float2 *corr = reinterpret_cast<float2 *>(xfrag + TL_XFRAG_BYTES);   // per block: {zero-point correction, 2^20 / S_b}
+    // (behind the fragments: per block {zero-point correction, 2^20 / S_b}, see gemv_phase)
     AttnT &att = *reinterpret_cast<AttnT *>(xfrag);   // the attention phase has no GEMV input: same bytes
 
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
@@ -958,7 +957,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     }
 
     // ===================== math warps =====================
-    const int g = lane >> 2, t = lane & 3;
     int it = 0;
     if (warp == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.phases[0]);
@@ -977,7 +975,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         // instead of being carried in registers across the phase (they were spilled to local memory: an L2 trip each, see input_frags).
         const TilePhase &P = sh.ph[p % 3];
         const int kind = P.kind, nbg = P.nbg;
-        const unsigned int magic = P.nbg_magic;
         int u0, u1;
         band_of(P.units, blockIdx.x, G, A.g_magic, u0, u1);
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
