@@ -1301,13 +1301,11 @@ int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int
 int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, float *ms_out) {
     int rc = ready(m); if (rc) return rc;
     if (!ms_out || n_steps <= 0 || pos0 < 0 || pos0 + n_steps > m->c.seq_len || token < 0 || token >= m->c.vocab_size) return fail(NL_ERR_INVALID, "bad argument");
-    int32_t p = pos0 - 1;  // argmax_advance pre-increments
-    // seed: logits currently on the device decide the first token unless we overwrite; do one plain forward first
+    // the first step is a plain forward of (token, pos0); every later step takes the argmax of the step before and the next position
     m->h_stage[0] = token; m->h_stage[64] = pos0;
     NL_CUDA(cudaMemcpyAsync(m->d_token, m->h_stage, 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + 64, 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemsetAsync(m->d_gen_count, 0, 4, m->st));
-    (void)p;
     NL_CUDA(cudaEventRecord(m->ev0, m->st));
     NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
     for (int i = 1; i < n_steps; i++) NL_CUDA(cudaGraphLaunch(m->g_step[1], m->st));
