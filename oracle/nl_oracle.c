@@ -512,6 +512,89 @@ float *nlo_key_cache(nlo_model *m) { return m->kc; }
 float *nlo_value_cache(nlo_model *m) { return m->vc; }
 float *nlo_rope_cos(nlo_model *m) { return m->cosc; }
 float *nlo_rope_sin(nlo_model *m) { return m->sinc; }
+/* ---- sampling step of Engine.Generate (go/main.go:177-197, :294-398).  r01 = the value rng.Float32() delivers (the Go generator itself
+ * is not restated: the callers pass the same number to both sides).  Plain restatements: the O(vocab * k) insertion of sampleTopK, a
+ * full sort in sampleTopP (the reference's sort.Slice is unstable; ties are broken by index here). ---- */
+void nlo_rep_penalty(float *logits, int vocab, const int32_t *recent, int n_recent, float penalty) {   /* go/main.go:177-187 */
+    if (!(penalty > 1.0f)) return;
+    for (int i = 0; i < n_recent; i++) {
+        int tok = recent[i];
+        if (tok >= 0 && tok < vocab) {
+            if (logits[tok] > 0) logits[tok] /= penalty; else logits[tok] *= penalty;
+        }
+    }
+}
+int nlo_sample_top_k(const float *logits, int vocab, float temp, int top_k, float r01) {   /* go/main.go:294-343 */
+    if (temp <= 0 || top_k < 1) return nlo_argmax(logits, vocab);   /* (top_k < 1 panics in the reference) */
+    if (top_k > vocab) top_k = vocab;
+    int *idx = malloc(sizeof(int) * (size_t)top_k);
+    float *val = malloc(sizeof(float) * (size_t)top_k), *probs = malloc(sizeof(float) * (size_t)top_k);
+    for (int i = 0; i < top_k; i++) { idx[i] = -1; val[i] = -1e30f; }
+    for (int i = 0; i < vocab; i++) {
+        if (logits[i] > val[top_k - 1]) {
+            idx[top_k - 1] = i; val[top_k - 1] = logits[i];
+            for (int j = top_k - 1; j > 0 && val[j] > val[j - 1]; j--) {
+                int ti = idx[j]; idx[j] = idx[j - 1]; idx[j - 1] = ti;
+                float tv = val[j]; val[j] = val[j - 1]; val[j - 1] = tv;
+            }
+        }
+    }
+    float maxv = val[0], sum = 0.f;
+    int n = 0;
+    for (int i = 0; i < top_k; i++) {
+        if (idx[i] < 0) break;
+        probs[i] = (float)exp((double)((val[i] - maxv) / temp));
+        sum += probs[i];
+        n = i + 1;
+    }
+    for (int i = n; i < top_k; i++) probs[i] = 0.f;
+    float r = r01 * sum, cdf = 0.f;
+    int res = n > 0 ? idx[0] : 0;
+    for (int i = 0; i < top_k; i++) {
+        cdf += probs[i];
+        if (r <= cdf) { res = idx[i]; break; }
+    }
+    free(idx); free(val); free(probs);
+    return res;
+}
+typedef struct { int idx; float prob; } idx_prob;
+static int cmp_prob_desc(const void *a, const void *b) {
+    const idx_prob *x = a, *y = b;
+    if (x->prob > y->prob) return -1;
+    if (x->prob < y->prob) return 1;
+    return x->idx - y->idx;
+}
+int nlo_sample_top_p(const float *logits, int vocab, float temp, float top_p, float r01) {   /* go/main.go:346-398 */
+    if (temp <= 0) return nlo_argmax(logits, vocab);
+    float maxv = logits[0];
+    for (int i = 1; i < vocab; i++) if (logits[i] > maxv) maxv = logits[i];
+    idx_prob *c = malloc(sizeof(idx_prob) * (size_t)vocab);
+    float sum = 0.f;
+    for (int i = 0; i < vocab; i++) {
+        float p = (float)exp((double)((logits[i] - maxv) / temp));
+        c[i].idx = i; c[i].prob = p;
+        sum += p;
+    }
+    float inv = 1.0f / sum;
+    for (int i = 0; i < vocab; i++) c[i].prob *= inv;
+    qsort(c, (size_t)vocab, sizeof(idx_prob), cmp_prob_desc);
+    float cum = 0.f;
+    int res = c[0].idx;
+    for (int i = 0; i < vocab; i++) {
+        cum += c[i].prob;
+        if (cum >= top_p) {
+            float r = r01 * cum, cdf = 0.f;
+            for (int j = 0; j <= i; j++) {
+                cdf += c[j].prob;
+                if (r <= cdf) { res = c[j].idx; break; }
+            }
+            break;
+        }
+    }
+    free(c);
+    return res;
+}
+
 
 /* Greedy loop of Engine.Generate with temp<=0, rep-penalty 1.0 (go/main.go:152-230): prefill token by token
  * (stops at seq_len-1), then argmax / forward until n_new tokens, EOS, or pos reaches seq_len.

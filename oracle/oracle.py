@@ -51,6 +51,9 @@ def lib():
         L.nlo_silu.restype = C.c_float
         L.nlo_silu.argtypes = [C.c_float]
         L.nlo_argmax.argtypes = [C.c_void_p, C.c_int]
+        L.nlo_rep_penalty.argtypes = [C.c_void_p, C.c_int, C.c_void_p, C.c_int, C.c_float]
+        L.nlo_sample_top_k.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_int, C.c_float]
+        L.nlo_sample_top_p.argtypes = [C.c_void_p, C.c_int, C.c_float, C.c_float, C.c_float]
         L.nlo_model_new.restype = C.c_void_p
         L.nlo_model_new.argtypes = [C.POINTER(NloConfig)]
         L.nlo_model_free.argtypes = [C.c_void_p]
@@ -113,6 +116,26 @@ def softmax(x):
 
 def silu(x: float) -> float:
     return lib().nlo_silu(float(x))
+
+
+def rep_penalty(logits: np.ndarray, recent, penalty: float) -> np.ndarray:
+    """go/main.go:177-187 on a copy of `logits`."""
+    out = np.ascontiguousarray(logits, dtype=np.float32).copy()
+    r = np.ascontiguousarray(recent, dtype=np.int32)
+    lib().nlo_rep_penalty(_p(out), out.size, _p(r) if r.size else None, r.size, float(penalty))
+    return out
+
+
+def sample_top_k(logits: np.ndarray, temp: float, top_k: int, r01: float) -> int:
+    """sampleTopK, go/main.go:294-343; r01 stands for rng.Float32()."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    return int(lib().nlo_sample_top_k(_p(lg), lg.size, float(temp), int(top_k), float(r01)))
+
+
+def sample_top_p(logits: np.ndarray, temp: float, top_p: float, r01: float) -> int:
+    """sampleTopP, go/main.go:346-398; r01 stands for rng.Float32()."""
+    lg = np.ascontiguousarray(logits, dtype=np.float32)
+    return int(lib().nlo_sample_top_p(_p(lg), lg.size, float(temp), float(top_p), float(r01)))
 
 
 class OracleModel:

@@ -491,7 +491,7 @@ def test_device_sampling_matches_host_samplers():
     m = _sampling_model()
     host = Engine(m, seed=0)
     logits = m.state.logits.copy()
-    bad, total = [], 0
+    bad, bad_oracle, total = [], [], 0
     for temp, top_k, top_p in [(0.8, 50, 0.9), (1.0, 40, 1.0), (0.7, 5, 1.0), (1.3, 3000, 1.0), (0.9, 50, 0.5), (2.5, 50, 0.99), (0.0, 50, 0.9)]:
         for u in (0.0, 0.013, 0.25, 0.5, 0.77, 0.9991):
             m.state.logits[:] = logits
@@ -501,7 +501,11 @@ def test_device_sampling_matches_host_samplers():
             total += 1
             if got != exp:
                 bad.append((temp, top_k, top_p, u, exp, got))
+            ora = O.sample_top_p(logits, temp, top_p, np.float32(u)) if top_p < 1.0 else O.sample_top_k(logits, temp, top_k, np.float32(u))
+            if ora != exp:   # the C oracle's restatement of the same samplers (tests/test_oracle.py ties the two on the CPU)
+                bad_oracle.append((temp, top_k, top_p, u, exp, ora))
     assert len(bad) <= 1, (bad[:5], total)
+    assert len(bad_oracle) <= 1, (bad_oracle[:5], total)
     # the logits were not touched (no repetition penalty asked for)
     assert np.array_equal(m.get_logits(), logits)
     m.close()

@@ -125,3 +125,29 @@ def test_forward_rejects_out_of_range(golden_dir):
         m.forward(256, 0)
     with pytest.raises(IndexError):
         m.forward(1, 64)
+
+
+def test_oracle_samplers_agree_with_the_host_mirror():
+    """Two restatements of go/main.go:177-197 / :294-398 -- the C oracle (insertion top-k, qsort top-p) and the host mirror in
+    nanollama_b200/engine.py (numpy stable sorts, fp32 loops) -- select the same token for the same random number; the GPU sampler
+    (nl_sample) is checked against both in tests/test_gpu_parity.py."""
+    from types import SimpleNamespace
+    from nanollama_b200.engine import Engine
+    rng = np.random.default_rng(12)
+    for n, scale in ((1000, 3.0), (4096, 1.0), (257, 8.0)):
+        lg = (rng.standard_normal(n) * scale).astype(np.float32)
+        lg[7] = lg[3]
+        model = SimpleNamespace(state=SimpleNamespace(logits=lg.copy()), config=SimpleNamespace(vocab_size=n))
+        host = Engine(model, seed=0)
+        for temp, top_k, top_p in [(0.8, 50, 0.9), (1.0, 40, 1.0), (0.7, 1, 1.0), (1.3, 600, 1.0), (0.9, 50, 0.5), (2.0, 50, 0.99), (0.0, 5, 0.9)]:
+            for u in (0.0, 0.13, 0.5, 0.77, 0.9991):
+                host.rng = SimpleNamespace(random=lambda: u)
+                if top_p < 1.0:
+                    assert O.sample_top_p(lg, temp, top_p, np.float32(u)) == host.sample_top_p(temp, top_p), (n, temp, top_p, u)
+                else:
+                    assert O.sample_top_k(lg, temp, top_k, np.float32(u)) == host.sample_top_k(temp, top_k), (n, temp, top_k, u)
+    # repetition penalty: once per occurrence, sign-dependent, out-of-range ids ignored
+    lg = np.array([2.0, -1.0, 0.0, 4.0], np.float32)
+    out = O.rep_penalty(lg, [0, 1, 0, 9, -1, 2], 2.0)
+    assert np.array_equal(out, np.array([0.5, -2.0, 0.0, 4.0], np.float32))
+    assert np.array_equal(O.rep_penalty(lg, [0, 1], 1.0), lg)
