@@ -22,6 +22,7 @@ import "C"
 
 import (
 	"fmt"
+	"runtime"
 	"unsafe"
 )
 
@@ -30,7 +31,12 @@ type cudaBackend struct {
 	h *C.nl_model
 }
 
-func nlErr(rc C.int, what string) error {
+// nlCall runs one ABI call and, on failure, fetches its message.  nl_last_error() is thread-local on the C side and a
+// goroutine may migrate between two cgo calls, so the call and the fetch run pinned to one OS thread.
+func nlCall(what string, f func() C.int) error {
+	runtime.LockOSThread()
+	defer runtime.UnlockOSThread()
+	rc := f()
 	if rc == C.NL_OK {
 		return nil
 	}
@@ -52,9 +58,13 @@ func (b *cudaBackend) uploadTensor(g *GGUFFile, slot C.int, layer int, name stri
 	for d := uint32(1); d < info.NDims; d++ {
 		rows *= int64(info.Dims[d])
 	}
-	rc := C.nl_upload_tensor(b.h, slot, C.int(layer), C.uint32_t(info.Type), C.int64_t(rows), C.int64_t(cols),
-		unsafe.Pointer(&data[0]), C.size_t(len(data)))
-	return true, nlErr(rc, name)
+	if len(data) == 0 {
+		return false, fmt.Errorf("%s: empty tensor", name)
+	}
+	return true, nlCall(name, func() C.int {
+		return C.nl_upload_tensor(b.h, slot, C.int(layer), C.uint32_t(info.Type), C.int64_t(rows), C.int64_t(cols),
+			unsafe.Pointer(&data[0]), C.size_t(len(data)))
+	})
 }
 
 // LoadLlamaModelCUDA replaces LoadLlamaModel (model.go:121-174): same config defaulting, same tensor names and
@@ -76,7 +86,7 @@ func LoadLlamaModelCUDA(g *GGUFFile, device int) (*LlamaModel, error) {
 		cfg.rope_conjugate = 1
 	}
 	b := &cudaBackend{}
-	if err := nlErr(C.nl_create(&cfg, &b.h), "create"); err != nil {
+	if err := nlCall("create", func() C.int { return C.nl_create(&cfg, &b.h) }); err != nil {
 		return nil, err
 	}
 	fail := func(err error) (*LlamaModel, error) {
@@ -113,7 +123,7 @@ func LoadLlamaModelCUDA(g *GGUFFile, device int) (*LlamaModel, error) {
 			}
 		}
 	}
-	if err := nlErr(C.nl_finalize(b.h), "finalize"); err != nil {
+	if err := nlCall("finalize", func() C.int { return C.nl_finalize(b.h) }); err != nil {
 		C.nl_destroy(b.h)
 		return nil, err
 	}
@@ -137,16 +147,49 @@ func LoadLlamaModelCUDA(g *GGUFFile, device int) (*LlamaModel, error) {
 // Forward keeps the reference signature (model.go:490): no return value, result in State.Logits.
 // The reference panics on an out-of-range slice index; so does this.
 func (m *LlamaModel) Forward(token int, pos int) {
-	rc := C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), (*C.float)(unsafe.Pointer(&m.State.Logits[0])))
-	if rc != C.NL_OK {
-		panic(nlErr(rc, "Forward"))
+	err := nlCall("Forward", func() C.int {
+		return C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), (*C.float)(unsafe.Pointer(&m.State.Logits[0])))
+	})
+	if err != nil {
+		panic(err)
 	}
+}
+
+// SetGammaCUDA pushes a loaded personality (gamma.go:22-35) to the device, where the embedding kernel adds row
+// IndexMap[token] to the embedding exactly like ApplyToEmbedding (gamma.go:272-290, model.go:502-505); nil removes it.
+// Call it wherever the reference assigns model.Gamma (main.go:79): `model.Gamma = gamma; model.SetGammaCUDA(gamma)`.
+func (m *LlamaModel) SetGammaCUDA(g *GammaEssence) error {
+	if g == nil || g.NumTokens == 0 {
+		return nlCall("set_gamma", func() C.int { return C.nl_set_gamma(m.cuda.h, nil, 0, nil) })
+	}
+	if g.EmbedDim != m.Config.EmbedDim {
+		return fmt.Errorf("gamma embed_dim %d != model dim %d", g.EmbedDim, m.Config.EmbedDim)
+	}
+	n := g.NumTokens * g.EmbedDim
+	rows := make([]C.float, n)
+	for i := 0; i < n; i++ {
+		if g.IsF16 {
+			rows[i] = C.float(half2float(g.ValuesF16[i]))
+		} else {
+			rows[i] = C.float(g.Values[i])
+		}
+	}
+	t2r := make([]C.int32_t, m.Config.VocabSize)
+	for i := range t2r {
+		t2r[i] = -1
+	}
+	for tok, row := range g.IndexMap {
+		if int(tok) >= 0 && int(tok) < len(t2r) {
+			t2r[tok] = C.int32_t(row)
+		}
+	}
+	return nlCall("set_gamma", func() C.int { return C.nl_set_gamma(m.cuda.h, &rows[0], C.int32_t(g.NumTokens), &t2r[0]) })
 }
 
 // Reset keeps model.go:623-631: zero both KV caches, Pos = 0.
 func (m *LlamaModel) Reset() {
-	if rc := C.nl_reset(m.cuda.h); rc != C.NL_OK {
-		panic(nlErr(rc, "Reset"))
+	if err := nlCall("Reset", func() C.int { return C.nl_reset(m.cuda.h) }); err != nil {
+		panic(err)
 	}
 	m.State.Pos = 0
 }
@@ -154,14 +197,22 @@ func (m *LlamaModel) Reset() {
 // GenerateGreedyCUDA is the optional fast path for `--temp 0 --rep-penalty 1.0`: the whole loop of Engine.Generate
 // (main.go:152-230) stays on the device (argmax with the first-maximum tie rule of main.go:400-408).
 func (m *LlamaModel) GenerateGreedyCUDA(prompt []int, maxTokens, eosID int) ([]int, error) {
+	if len(prompt) == 0 {
+		return nil, fmt.Errorf("generate: empty prompt")
+	}
+	if maxTokens <= 0 {
+		return []int{}, nil
+	}
 	p := make([]C.int32_t, len(prompt))
 	for i, t := range prompt {
 		p[i] = C.int32_t(t)
 	}
 	out := make([]C.int32_t, maxTokens)
 	var n C.int32_t
-	rc := C.nl_generate_greedy(m.cuda.h, &p[0], C.int32_t(len(p)), C.int32_t(maxTokens), C.int32_t(eosID), &out[0], &n)
-	if err := nlErr(rc, "generate"); err != nil {
+	err := nlCall("generate", func() C.int {
+		return C.nl_generate_greedy(m.cuda.h, &p[0], C.int32_t(len(p)), C.int32_t(maxTokens), C.int32_t(eosID), &out[0], &n)
+	})
+	if err != nil {
 		return nil, err
 	}
 	res := make([]int, int(n))
@@ -173,8 +224,8 @@ func (m *LlamaModel) GenerateGreedyCUDA(prompt []int, maxTokens, eosID int) ([]i
 
 // ForwardDeviceCUDA is Forward with the logits left on the device (State.Logits is not refreshed): the companion of SampleCUDA.
 func (m *LlamaModel) ForwardDeviceCUDA(token, pos int) {
-	if rc := C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), nil); rc != C.NL_OK {
-		panic(nlErr(rc, "Forward"))
+	if err := nlCall("Forward", func() C.int { return C.nl_forward(m.cuda.h, C.int32_t(token), C.int32_t(pos), nil) }); err != nil {
+		panic(err)
 	}
 }
 
@@ -192,8 +243,10 @@ func (m *LlamaModel) SampleCUDA(temp float32, topK int, topP, repPenalty float32
 		rp = &rec[0]
 	}
 	var tok C.int32_t
-	rc := C.nl_sample(m.cuda.h, C.float(temp), C.int32_t(topK), C.float(topP), C.float(repPenalty), rp, C.int32_t(len(rec)), C.float(u), &tok)
-	if err := nlErr(rc, "sample"); err != nil {
+	err := nlCall("sample", func() C.int {
+		return C.nl_sample(m.cuda.h, C.float(temp), C.int32_t(topK), C.float(topP), C.float(repPenalty), rp, C.int32_t(len(rec)), C.float(u), &tok)
+	})
+	if err != nil {
 		return 0, err
 	}
 	return int(tok), nil

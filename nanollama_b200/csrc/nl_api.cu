@@ -12,7 +12,6 @@
 #include "nl_gemv.cuh"
 #include "nl_kernels.cuh"
 #include "nl_stream.cuh"
-#include "nl_mega.cuh"
 #include "nl_tile.cuh"
 #include "nl_sample.cuh"
 #include <string>
@@ -266,12 +265,8 @@ struct nl_model {
     // one-pass prefill workspace (allocated on first use, sized for seq_len rows)
     float *pf_x = nullptr, *pf_qkv = nullptr, *pf_g = nullptr, *pf_u = nullptr; __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr; int pf_cap = 0;
     DevMat lm_view;   // this rank's vocab rows of the LM head (a view into output / tok_embd when tied; never freed)
-    // per-token persistent kernel (batch 1)
-    bool mega_ok = false;
-    MegaPhase *d_phases = nullptr; unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;
-    MegaArgs margs; int mega_grid = 0; size_t mega_smem = 0; int mega_type = -1;
+    unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;   // grid-barrier counters, split-attention partials
     unsigned long long *d_trace = nullptr, *d_trace2 = nullptr;
-    int mega_reps = 1;
     // tiled tensor-core decode (nl_tile.cuh): fragment-tiled copies of the Q4_0 matrices, batch 1, single GPU
     bool tile_ok = false; int tile_type = NL_Q4_0;
     std::vector<uint8_t *> tile_bufs;   // per layer: qkv, o, gate/up, down; then the LM head
@@ -283,8 +278,6 @@ struct nl_model {
     float2 *amax = nullptr; bool amax_valid = false;   // per-CTA argmax pairs of the LM-head phase
     float *qkv_bias = nullptr;
     TilePhase *d_tphases = nullptr; TileArgs targs; int tile_grid = 0;
-    int act_stride = 0;          // floats between the MG_REPS copies of x / xb2 / hb (replica 0 is what every other path uses)
-    float *attn_out = nullptr;   // xb2 with replicas
 };
 
 static int set_dev(const nl_model *m) {
@@ -305,109 +298,6 @@ static int upload_vec(float **dst, int type, int64_t n, const void *host, size_t
     if (rc == NL_OK && cudaStreamSynchronize(st) != cudaSuccess) rc = fail(NL_ERR_CUDA, "dequant vector failed");
     free_mat(tmp);
     return rc;
-}
-
-// Plan one GEMV phase of the persistent kernel; returns false when the shape cannot be tiled for it.
-static bool plan_mega_gemv(MegaPhase &P, int type, const MatRef *mats, int nmat, int NM, int epi, int xsrc, const float *x, const float *norm_w,
-                           int x_reps, int out_reps, int stride) {
-    const DevMat &w0 = *mats[0].w;
-    const int QB = type == NL_Q4_0 ? 16 : type == NL_Q8_0 ? 32 : 64, DB = type == NL_F16 ? 0 : 2;
-    memset(&P, 0, sizeof P);
-    P.kind = PH_GEMV; P.nseg = nmat; P.x = x; P.norm_w = norm_w; P.xsrc = xsrc; P.epi = epi; P.NM = NM;
-    P.x_reps = x_reps; P.x_stride = stride; P.out_reps = out_reps; P.out_stride = stride;
-    P.cols = (int)w0.cols; P.nb = P.cols / 32; P.nb_pad = (P.nb + 31) / 32 * 32;
-    if (P.cols % 32 || P.nb_pad > MG_CONSUMERS) return false;
-    P.RG = MG_CONSUMERS / P.nb_pad;
-    if (DB && ((P.RG * P.nb * DB) % 16)) return false;            // every chunk's scale-plane slice must be a 16-byte multiple
-    P.upc = 4 / NM;
-    while (P.upc > 1 && NM * P.upc * P.RG * P.nb * (QB + DB) > 56 * 1024) P.upc >>= 1;
-    P.upc_log2 = P.upc == 4 ? 2 : P.upc == 2 ? 1 : 0;
-    P.q_chunk_bytes = P.upc * P.RG * P.nb * QB; P.d_chunk_bytes = P.upc * P.RG * P.nb * DB;
-    if (NM * (P.q_chunk_bytes + P.d_chunk_bytes) > 56 * 1024) return false;
-    int units = 0;
-    for (int i = 0; i < nmat; i++) {
-        const DevMat &w = *mats[i].w;
-        if (w.type != type || w.cols != w0.cols) return false;
-        if (NM == 2 && (mats[i].w2->type != type || mats[i].w2->cols != w0.cols || mats[i].w2->rows != w.rows)) return false;
-        if (DB && ((w.rows * P.nb * DB) % 16)) return false;
-        P.seg[i].qs = w.qs; P.seg[i].d = w.d;
-        if (NM == 2) { P.seg[i].qs2 = mats[i].w2->qs; P.seg[i].d2 = mats[i].w2->d; }
-        P.seg[i].bias = mats[i].bias; P.seg[i].out = mats[i].out; P.seg[i].rows = (int)w.rows; P.seg[i].tile_begin = units;
-        P.seg_units[i] = (int)((w.rows + P.RG - 1) / P.RG);
-        units += P.seg_units[i];
-    }
-    P.total_units = units;
-    return true;
-}
-
-// Build the phase list of the per-token persistent kernel (see nl_mega.cuh).  Leaves mega_ok=false when the model does not fit
-// its constraints (mixed tensor types, raw-block types, head_dim != 64, GQA group > 8, ...): the multi-kernel path is used then.
-static int build_mega(nl_model *m) {
-    const nl_config &c = m->c;
-    m->mega_ok = false;
-    // Opt-in (NL_MEGA=1): on B200 the persistent kernel currently trails the PDL-chained per-matrix kernels
-    if (!getenv("NL_MEGA") || getenv("NL_NO_MEGA") || m->tp > 1) return NL_OK;
-    const int type = m->L[0].wq.type;
-    if (type != NL_Q4_0 && type != NL_Q8_0 && type != NL_F16) return NL_OK;
-    if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
-    const int G = m->opts.num_sms;
-    const int dim = m->dim, kvd = m->kvd, qdim = m->qdim, ffn = c.interm_size;
-    std::vector<MegaPhase> ph;
-    MegaPhase P;
-    int R = 1; const int S = m->act_stride;
-    if (getenv("NL_REPS")) { R = atoi(getenv("NL_REPS")); if (R < 1) R = 1; if (R > MG_REPS) R = MG_REPS; }
-    m->mega_reps = R;
-    for (int l = 0; l < c.n_layers; l++) {
-        Layer &ly = m->L[l];
-        MatRef qkv[3] = {{&ly.wq, nullptr, ly.bq, m->q, qdim}, {&ly.wk, nullptr, ly.bk, m->k, kvd}, {&ly.wv, nullptr, ly.bv, m->v, kvd}};
-        if (!plan_mega_gemv(P, type, qkv, 3, 1, SEPI_STORE, XS_RMSNORM, m->x, ly.attn_norm, R, 1, S)) return NL_OK;
-        ph.push_back(P);
-        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; ph.push_back(P);
-        MatRef o = {&ly.wo, nullptr, ly.bo, m->x, dim};
-        if (!plan_mega_gemv(P, type, &o, 1, 1, SEPI_RESID, XS_PLAIN, m->xb2, nullptr, R, R, S)) return NL_OK;
-        ph.push_back(P);
-        MatRef gu = {&ly.wgate, &ly.wup, nullptr, m->hb, ffn};
-        if (!plan_mega_gemv(P, type, &gu, 1, 2, SEPI_SWIGLU, XS_RMSNORM, m->x, ly.ffn_norm, R, R, S)) return NL_OK;
-        ph.push_back(P);
-        MatRef dn = {&ly.wdown, nullptr, nullptr, m->x, dim};
-        if (!plan_mega_gemv(P, type, &dn, 1, 1, SEPI_RESID, XS_PLAIN, m->hb, nullptr, R, R, S)) return NL_OK;
-        ph.push_back(P);
-    }
-    const DevMat &outw = m->output.present() ? m->output : m->tok_embd;
-    MatRef lm = {&outw, nullptr, nullptr, m->logits, c.vocab_size};
-    if (!plan_mega_gemv(P, type, &lm, 1, 1, SEPI_STORE, XS_RMSNORM, m->x, m->output_norm, R, 1, S)) return NL_OK;
-    ph.push_back(P);
-    int slot = 0;
-    for (auto &p : ph) if (p.kind == PH_GEMV) { int b = p.NM * (p.q_chunk_bytes + p.d_chunk_bytes); if (b > slot) slot = b; }
-    slot = (slot + 127) / 128 * 128;
-    int stages = (int)((168 * 1024) / slot);  // + ~38 KB static smem of the kernel, under the 227 KB per-CTA limit
-    if (stages > MG_MAX_STAGES) stages = MG_MAX_STAGES;
-    if (stages < 2) return NL_OK;
-    int nsplit = G / c.n_kv_heads;
-    if (nsplit < 1) nsplit = 1;
-    if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
-    NL_CUDA(cudaMalloc(&m->d_phases, ph.size() * sizeof(MegaPhase)));
-    NL_CUDA(cudaMemcpy(m->d_phases, ph.data(), ph.size() * sizeof(MegaPhase), cudaMemcpyHostToDevice));
-    const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
-    NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
-    NL_CUDA(cudaMalloc(&m->part_acc, (size_t)c.n_heads * nsplit * 64 * 4));
-    NL_CUDA(cudaMalloc(&m->part_ml, (size_t)c.n_heads * nsplit * 2 * 4));
-    MegaArgs &a = m->margs;
-    memset(&a, 0, sizeof a);
-    a.hold_mode = getenv("NL_HOLD") ? atoi(getenv("NL_HOLD")) : 0;
-    a.phases = m->d_phases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.stages = stages; a.slot_bytes = slot;
-    a.at.q = m->q; a.at.k = m->k; a.at.v = m->v; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
-    a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
-    a.at.n_heads = c.n_heads; a.at.n_kv_heads = c.n_kv_heads; a.at.seq_len = c.seq_len; a.at.qk_norm = c.qk_norm; a.at.conj = c.rope_conjugate;
-    a.at.nsplit = nsplit; a.at.out = m->xb2; a.at.out_reps = R; a.at.out_stride = S; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps; a.at.scale = (float)(1.0 / sqrt((double)m->hd));
-    if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
-        NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
-        NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
-        a.trace = m->d_trace;
-    }
-    m->mega_grid = G; m->mega_smem = (size_t)stages * slot; m->mega_type = type;
-    m->mega_ok = true;
-    return NL_OK;
 }
 
 // ---- tiled tensor-core decode path (nl_tile.cuh) ----
@@ -445,7 +335,7 @@ __global__ void bump_epoch_kernel(unsigned int *epoch) { *epoch += 1; }
 static int build_tiled(nl_model *m) {
     const nl_config &c = m->c;
     m->tile_ok = false;
-    if (getenv("NL_NO_TILED") || getenv("NL_MEGA")) return NL_OK;
+    if (getenv("NL_NO_TILED")) return NL_OK;
     const bool tpar = m->tp > 1;   // tensor parallel: the shards are tiled; o / down exchange their partials inside the kernel
     if (tpar && (getenv("NL_NO_TILED_TP") || !m->tp_ready)) return NL_OK;
     if (m->hd != 64 || c.n_heads / c.n_kv_heads > MG_MAX_GROUP) return NL_OK;
@@ -575,7 +465,7 @@ static int build_tiled(nl_model *m) {
         a.ar_off = m->tp_lay.ar_data; a.bar_off = m->tp_lay.tile_bar; a.lg_off = m->tp_lay.lg_data; a.amax_off = m->tp_lay.tile_amax;
         a.bar = reinterpret_cast<unsigned int *>(m->tp_win + m->tp_lay.tile_bar);
     }
-    a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_sh); a.at.out_reps = 1; a.at.out_stride = m->act_stride; a.at.split_cnt = m->d_bar + ph.size(); a.at.eps = c.rms_norm_eps;
+    a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_sh); a.at.eps = c.rms_norm_eps;
     a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
         NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
@@ -603,7 +493,7 @@ static int record_forward(nl_model *m, int batch) {
     int launches = 0;
     {   // 1. embedding (+gamma), model.go:500-507
         dim3 grid((dim + 255) / 256, batch);
-        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim, (batch == 1 && m->mega_ok) ? m->mega_reps : 1, m->act_stride);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim);
         launches++;
     }
     if (batch == 1 && m->tile_ok) {
@@ -615,18 +505,6 @@ static int record_forward(nl_model *m, int batch) {
         bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
         launches++;
         if (launch_tiled(m->tile_type, m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
-        launches++;
-        NL_CUDA(cudaGetLastError());
-        m->launches_fwd = launches;
-        return NL_OK;
-    }
-    if (batch == 1 && m->mega_ok) {
-        // everything after the embedding in ONE persistent kernel (nl_mega.cuh); its grid-barrier counters start at zero
-        NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->margs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
-        int rc = m->mega_type == NL_Q4_0 ? launch_mega_q4_0(m->margs, m->mega_grid, m->mega_smem, st)
-               : m->mega_type == NL_Q8_0 ? launch_mega_q8_0(m->margs, m->mega_grid, m->mega_smem, st)
-                                         : launch_mega_f16(m->margs, m->mega_grid, m->mega_smem, st);
-        if (rc) return fail(NL_ERR_CUDA, "persistent decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         launches++;
         NL_CUDA(cudaGetLastError());
         m->launches_fwd = launches;
@@ -670,7 +548,8 @@ static int record_forward(nl_model *m, int batch) {
             } else {
                 MatRef g = {&ly.wgate, nullptr, nullptr, m->hb, ffn}, u = {&ly.wup, nullptr, nullptr, m->hb2, ffn};
                 int rc = gemv_dispatch(&g, 1, m->x, dim, batch, EPI_STORE, ly.ffn_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
-                rc = gemv_dispatch(&u, 1, m->xb, dim, batch, EPI_STORE, nullptr, eps, nullptr, o, st, &launches); if (rc) return rc;  // xb holds the normed input
+                // (the gate dispatch may have fused the norm into its prologue without touching xb: norm again, the same way)
+                rc = gemv_dispatch(&u, 1, m->x, dim, batch, EPI_STORE, ly.ffn_norm, eps, m->xb, o, st, &launches); if (rc) return rc;
                 int64_t n = (int64_t)batch * ffn;
                 swiglu_kernel<<<(unsigned)((n + 255) / 256), 256, 0, st>>>(m->hb, m->hb2, n);
                 launches++;
@@ -734,7 +613,7 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
     int launches = 0, rc;
     {
         dim3 grid((dim + 255) / 256, B);
-        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim, 1, m->act_stride);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_token, m->gamma, m->gamma_map, m->x, dim);
         launches++;
     }
     for (int l = 0; l < c.n_layers; l++) {
@@ -961,12 +840,17 @@ int nl_set_gamma(nl_model *m, const float *rows, int32_t n_rows, const int32_t *
     for (auto &g : m->g_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     if (m->gamma) { cudaFree(m->gamma); m->gamma = nullptr; }
     if (m->gamma_map) { cudaFree(m->gamma_map); m->gamma_map = nullptr; }
-    if (!rows) return NL_OK;
-    if (n_rows <= 0 || !token_to_row) return fail(NL_ERR_INVALID, "gamma: bad arguments");
-    NL_CUDA(cudaMalloc(&m->gamma, (size_t)n_rows * m->dim * 4));
-    NL_CUDA(cudaMalloc(&m->gamma_map, (size_t)m->c.vocab_size * 4));
-    NL_CUDA(cudaMemcpy(m->gamma, rows, (size_t)n_rows * m->dim * 4, cudaMemcpyHostToDevice));
-    NL_CUDA(cudaMemcpy(m->gamma_map, token_to_row, (size_t)m->c.vocab_size * 4, cudaMemcpyHostToDevice));
+    if (rows) {
+        if (n_rows <= 0 || !token_to_row) return fail(NL_ERR_INVALID, "gamma: bad arguments");
+        for (int t = 0; t < m->c.vocab_size; t++)   // the embedding kernel indexes the rows with these: a public ABI checks them
+            if (token_to_row[t] < -1 || token_to_row[t] >= n_rows) return fail(NL_ERR_INVALID, "gamma: token_to_row[%d] = %d outside [-1, %d)", t, token_to_row[t], n_rows);
+        NL_CUDA(cudaMalloc(&m->gamma, (size_t)n_rows * m->dim * 4));
+        NL_CUDA(cudaMalloc(&m->gamma_map, (size_t)m->c.vocab_size * 4));
+        NL_CUDA(cudaMemcpy(m->gamma, rows, (size_t)n_rows * m->dim * 4, cudaMemcpyHostToDevice));
+        NL_CUDA(cudaMemcpy(m->gamma_map, token_to_row, (size_t)m->c.vocab_size * 4, cudaMemcpyHostToDevice));
+    }
+    // nl_generate_greedy / nl_prefill / nl_bench_decode launch the batch-1 graphs directly: re-capture them now
+    if (m->finalized && (m->tp == 1 || m->tp_ready)) return build_graphs(m, 1);
     return NL_OK;
 }
 
@@ -987,14 +871,8 @@ int nl_finalize(nl_model *m) {
     }
     const int B = m->B, dim = m->dim, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, half = m->hd / 2, ffn = m->ffn;
     auto alloc = [&](float **p, size_t n) -> int { NL_CUDA(cudaMalloc(p, n * 4)); NL_CUDA(cudaMemset(*p, 0, n * 4)); return NL_OK; };
-    {   // x, xb2 and hb double as the replicated activation vectors of the persistent batch-1 kernel
-        int mx = dim > qdim ? dim : qdim; if (ffn > mx) mx = ffn;
-        m->act_stride = (mx + 31) / 32 * 32;
-    }
-    const size_t rep_floats = (size_t)MG_REPS * m->act_stride;
-    auto mx2 = [](size_t a, size_t b) { return a > b ? a : b; };
-    if ((rc = alloc(&m->x, mx2((size_t)B * dim, rep_floats))) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, mx2((size_t)B * qdim, rep_floats))) ||
-        (rc = alloc(&m->hb, mx2((size_t)B * ffn, rep_floats))) || (rc = alloc(&m->hb2, (size_t)B * ffn)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
+    if ((rc = alloc(&m->x, (size_t)B * dim)) || (rc = alloc(&m->xb, (size_t)B * dim)) || (rc = alloc(&m->xb2, (size_t)B * qdim)) ||
+        (rc = alloc(&m->hb, (size_t)B * ffn)) || (rc = alloc(&m->hb2, (size_t)B * ffn)) || (rc = alloc(&m->q, (size_t)B * qdim)) ||
         (rc = alloc(&m->k, (size_t)B * kvd)) || (rc = alloc(&m->v, (size_t)B * kvd)) || (m->tp == 1 && (rc = alloc(&m->logits, (size_t)B * c.vocab_size))) ||
         (rc = alloc(&m->kc, (size_t)B * c.n_layers * S * kvd)) || (rc = alloc(&m->vc, (size_t)B * c.n_layers * S * kvd)))
         return rc;
@@ -1048,8 +926,6 @@ int nl_finalize(nl_model *m) {
     }
     rc = build_tiled(m);
     if (rc) return rc;
-    rc = build_mega(m);
-    if (rc) return rc;
     rc = build_graphs(m, 1);
     if (rc) return rc;
     m->finalized = true;
@@ -1067,6 +943,7 @@ void nl_destroy(nl_model *m) {
         free_mat(ly.wq); free_mat(ly.wk); free_mat(ly.wv); free_mat(ly.wo); free_mat(ly.wgate); free_mat(ly.wup); free_mat(ly.wdown);
         cudaFree(ly.attn_norm); cudaFree(ly.ffn_norm); cudaFree(ly.bq); cudaFree(ly.bk); cudaFree(ly.bv); cudaFree(ly.bo);
     }
+    if (m->tp > 1) m->logits = nullptr;   // lives inside the exchange window, freed with it below
     float *fs[] = {m->output_norm, m->gamma, m->x, m->xb, m->xb2, m->hb, m->hb2, m->q, m->k, m->v, m->logits, m->kc, m->vc, m->cos_t, m->sin_t};
     for (float *p : fs) if (p) cudaFree(p);
     int32_t *is[] = {m->gamma_map, m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->d_prompt, m->d_cursor};
@@ -1074,7 +951,6 @@ void nl_destroy(nl_model *m) {
     if (m->tp > 1) {
         for (int r = 0; r < m->tp; r++) if (r != m->rank && m->tp_peers.win[r]) cudaIpcCloseMemHandle(m->tp_peers.win[r]);
         if (m->tp_win) cudaFree(m->tp_win);
-        m->logits = nullptr;   // lived inside the window
         if (m->partial) cudaFree(m->partial);
         if (m->logits_local) cudaFree(m->logits_local);
         if (m->d_ar_epoch) cudaFree(m->d_ar_epoch);
@@ -1087,7 +963,6 @@ void nl_destroy(nl_model *m) {
     for (void *q : {(void *)m->x_sh, (void *)m->qkv_sh, (void *)m->ao_sh, (void *)m->hb_sh, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
     if (m->d_tphases) cudaFree(m->d_tphases);
-    if (m->d_phases) cudaFree(m->d_phases);
     if (m->d_bar) cudaFree(m->d_bar);
     if (m->part_acc) cudaFree(m->part_acc);
     if (m->part_ml) cudaFree(m->part_ml);
@@ -1146,7 +1021,7 @@ int nl_sample(nl_model *m, float temperature, int32_t top_k, float top_p, float 
     if (!token_out || n_recent < 0 || (n_recent > 0 && !recent)) return fail(NL_ERR_INVALID, "bad argument");
     if (n_recent > nl_model::SP_RECENT_CAP) return fail(NL_ERR_INVALID, "repetition window of %d tokens exceeds %d", n_recent, nl_model::SP_RECENT_CAP);
     if (temperature > 0.f && !(top_p < 1.0f) && top_k < 1) return fail(NL_ERR_INVALID, "top_k must be >= 1");
-    if (!(u >= 0.f && u < 1.f)) return fail(NL_ERR_INVALID, "u must be in [0, 1)");
+    if (temperature > 0.f && !(u >= 0.f && u < 1.f)) return fail(NL_ERR_INVALID, "u must be in [0, 1)");   // (ignored by the greedy step)
     const int vocab = m->c.vocab_size;
     if (!m->sp_keys) {
         NL_CUDA(cudaMalloc(&m->sp_keys, (size_t)vocab * 2 * sizeof(uint32_t)));
@@ -1210,7 +1085,7 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     NL_CUDA(cudaStreamSynchronize(st));   // tokens is caller memory
     {
         dim3 grid((dim + 255) / 256, n);
-        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_prompt, m->gamma, m->gamma_map, m->pf_x, dim, 1, 0);
+        embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_prompt, m->gamma, m->gamma_map, m->pf_x, dim);
     }
     int rc;
     for (int l = 0; l < c.n_layers; l++) {
@@ -1313,7 +1188,7 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
     NL_CUDA(cudaStreamSynchronize(m->st));
     NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
     if (m->d_trace && getenv("NL_TRACE")) {
-        const int tg = m->tile_ok ? m->tile_grid : m->mega_grid, tp_ = m->tile_ok ? m->targs.n_phases : m->margs.n_phases;
+        const int tg = m->tile_grid, tp_ = m->targs.n_phases;
         size_t n = (size_t)tg * tp_ * 8;
         std::vector<unsigned long long> h(n);
         NL_CUDA(cudaMemcpy(h.data(), m->d_trace, n * 8, cudaMemcpyDeviceToHost));
@@ -1334,7 +1209,7 @@ int nl_launches_per_token(const nl_model *m) { return m ? m->launches_fwd + 1 : 
 int64_t nl_weight_bytes(const nl_model *m) { return m ? m->weight_bytes : 0; }
 const char *nl_decode_path(const nl_model *m) {
     if (!m) return "";
-    return m->tile_ok ? "decode_tiled_kernel" : m->mega_ok ? "decode_mega_kernel" : "gemv_stream_kernel chain";
+    return m->tile_ok ? "decode_tiled_kernel" : "gemv_stream_kernel chain";
 }
 
 // ---- operator-level hooks ----

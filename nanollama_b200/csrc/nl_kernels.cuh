@@ -150,7 +150,7 @@ static __global__ void gemv_raw_kernel(int type, const uint8_t *__restrict__ raw
 // Embedding row lookup (+ optional gamma row add): embedLookupInto, go/model.go:389-446, :503-507
 // =====================================================================================================
 static __global__ void embed_kernel(DevMat e, const int32_t *__restrict__ tokens, const float *__restrict__ gamma, const int32_t *__restrict__ gamma_map,
-                             float *__restrict__ x, int dim, int reps, int rep_stride) {
+                             float *__restrict__ x, int dim) {
     const int b = blockIdx.y;
     const int tok = tokens[b];
     float *o = x + (int64_t)b * dim;
@@ -173,7 +173,6 @@ static __global__ void embed_kernel(DevMat e, const int32_t *__restrict__ tokens
         }
         if (gamma_map) { int g = gamma_map[tok]; if (g >= 0) v += gamma[(int64_t)g * dim + i]; }
         o[i] = v;
-        for (int r = 1; r < reps; r++) o[(int64_t)r * rep_stride + i] = v;  // replicas read by the persistent decode kernel
     }
 }
 

@@ -34,10 +34,45 @@
 
 #include "nl_common.cuh"
 #include "nl_stream.cuh"  // PTX wrappers
-#include "nl_mega.cuh"    // MegaAttn, attn_item, grid-barrier helpers
 #include "nl_tp.cuh"      // TpPeers: peer windows of a tensor-parallel group
 
 namespace nl {
+
+constexpr int MG_MAX_GROUP = 8;                    // q heads per kv head handled by one attention item
+constexpr int MG_MAX_SPLIT = 16;                   // splits of the context per kv head (flash-decoding partials)
+enum { PH_GEMV = 0, PH_ATTN = 1 };
+
+// what the attention phase needs besides its descriptor (go/model.go:530-587)
+struct MegaAttn {
+    const float *q, *k, *v;      // q is the base of this layer's q | k | v vector; k / v only carry element offsets from it
+    float *kcache, *vcache;      // [L][S][kvd]
+    const float *cos_t, *sin_t;  // [S][hd/2]
+    const int32_t *pos;          // device scalar
+    float *part_acc;             // [H][nsplit][hd]   un-normalised partial outputs (flagged pairs)
+    float *part_ml;              // [H][nsplit][2]    (running max, sum of exp)
+    float *out;
+    int n_heads, n_kv_heads, seq_len, qk_norm, conj, nsplit;
+    float eps, scale;
+};
+
+__device__ __forceinline__ unsigned int ld_acquire(const unsigned int *p) {
+    unsigned int v;
+    asm volatile("ld.acquire.gpu.global.u32 %0, [%1];" : "=r"(v) : "l"(p) : "memory");
+    return v;
+}
+// Grid barrier (barrier mode only): every CTA adds 1 to the phase's counter after its last output of that phase (release); one thread
+// per CTA polls the counter (acquire).  Counters are zeroed by a memset node in front of the kernel.
+__device__ __forceinline__ void phase_arrive(unsigned int *bar, int p) {
+    asm volatile("red.release.gpu.global.add.u32 [%0], 1;" ::"l"(bar + p) : "memory");
+}
+__device__ __forceinline__ void phase_wait(const unsigned int *bar, int p, unsigned int G) {
+    while (ld_acquire(bar + p) < G) { __nanosleep(20); }
+}
+__device__ __forceinline__ unsigned long long gtime() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
 
 constexpr int TL_CW = 16;                          // math warps
 constexpr int TL_CONSUMERS = TL_CW * 32;           // 512
