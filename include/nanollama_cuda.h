@@ -145,11 +145,14 @@ void nl_matrix_destroy(nl_matrix *w);
 /* Runs n_steps decode steps (device-side greedy feedback, starting from `token` at `pos0`) and returns the CUDA-event
  * time of the whole span in ms.  No host<->device traffic inside the timed region. */
 int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, float *ms_out);
+/* nl_prefill of device-resident work only: the n tokens are copied to the device first, then the prefill's kernels are timed with
+ * CUDA events on the library's stream (ms_out); no logits leave the device.  *launches_out (optional) = kernels launched. */
+int nl_bench_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *ms_out, int32_t *launches_out);
 /* number of kernel launches one decode step issues (graph nodes) */
 int nl_launches_per_token(const nl_model *m);
 /* bytes of weights resident on this device (after sharding) */
 int64_t nl_weight_bytes(const nl_model *m);
-/* name of the kernel family that executes a batch-1 Forward of this model ("decode_tiled_kernel", "decode_mega_kernel",
+/* name of the kernel family that executes a batch-1 Forward of this model ("decode_tiled_kernel",
  * "gemv_stream_kernel chain"); static string */
 const char *nl_decode_path(const nl_model *m);
 

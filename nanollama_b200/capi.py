@@ -58,6 +58,7 @@ SIGNATURES = {
     "nl_matrix_bench": (C.c_int, [_vp, _i32, _i32, _i32, _i32, C.POINTER(C.c_float)]),
     "nl_matrix_destroy": (None, [_vp]),
     "nl_bench_decode": (C.c_int, [_vp, _i32, _i32, _i32, C.POINTER(C.c_float)]),
+    "nl_bench_prefill": (C.c_int, [_vp, _vp, _i32, _i32, C.POINTER(C.c_float), C.POINTER(_i32)]),
     "nl_launches_per_token": (C.c_int, [_vp]),
     "nl_weight_bytes": (_i64, [_vp]),
     "nl_decode_path": (C.c_char_p, [_vp]),

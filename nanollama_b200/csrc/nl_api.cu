@@ -264,6 +264,7 @@ struct nl_model {
     unsigned int *d_ar_epoch = nullptr, *d_lg_epoch = nullptr;
     // one-pass prefill workspace (allocated on first use, sized for seq_len rows)
     float *pf_x = nullptr, *pf_qkv = nullptr, *pf_g = nullptr, *pf_u = nullptr; __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr; int pf_cap = 0;
+    bool pf_time = false; int pf_launches = 0;   // nl_bench_prefill: event after the token copy, kernels launched by the last prefill
     DevMat lm_view;   // this rank's vocab rows of the LM head (a view into output / tok_embd when tied; never freed)
     unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;   // grid-barrier counters, split-attention partials
     unsigned long long *d_trace = nullptr, *d_trace2 = nullptr;
@@ -1060,10 +1061,12 @@ static int prefill_sequential(nl_model *m, const int32_t *tokens, int n, int pos
     NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemsetAsync(m->d_cursor, 0, 4, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));  // tokens is caller memory: the copy must be done before we return or reuse it
+    if (m->pf_time) NL_CUDA(cudaEventRecord(m->ev0, m->st));
     for (int i = 0; i < n; i++) {
         feed_prompt_kernel<<<1, 1, 0, m->st>>>(m->d_prompt, m->d_cursor, pos0, m->d_token, m->d_pos);
         NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
     }
+    m->pf_launches = n * (m->launches_fwd + 1);
     NL_CUDA(cudaGetLastError());
     return NL_OK;
 }
@@ -1083,10 +1086,12 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     { int rc0 = ensure_pf(m); if (rc0) return rc0; }
     NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     NL_CUDA(cudaStreamSynchronize(st));   // tokens is caller memory
+    if (m->pf_time) NL_CUDA(cudaEventRecord(m->ev0, st));
     {
         dim3 grid((dim + 255) / 256, n);
         embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_prompt, m->gamma, m->gamma_map, m->pf_x, dim);
     }
+    m->pf_launches = 1 + c.n_layers * 12 + 1;   // embedding; per layer 2 norms, 7 GEMMs, RoPE/KV write, attention, SwiGLU split; LM-head GEMV
     int rc;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
@@ -1122,15 +1127,37 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     return NL_OK;
 }
 
-int nl_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *logits_last) {
-    int rc = ready(m); if (rc) return rc;
+static int prefill_check(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0) {
     if (!tokens || n <= 0) return fail(NL_ERR_INVALID, "empty prompt");
     if (pos0 < 0 || pos0 + n > m->c.seq_len) return fail(NL_ERR_INVALID, "positions [%d,%d) exceed seq_len %d", pos0, pos0 + n, m->c.seq_len);
     for (int i = 0; i < n; i++) if (tokens[i] < 0 || tokens[i] >= m->c.vocab_size) return fail(NL_ERR_INVALID, "token %d out of range", tokens[i]);
+    return NL_OK;
+}
+
+int nl_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *logits_last) {
+    int rc = ready(m); if (rc) return rc;
+    rc = prefill_check(m, tokens, n, pos0); if (rc) return rc;
     rc = prefill_gemm_ok(m, n) ? prefill_gemm(m, tokens, n, pos0) : prefill_sequential(m, tokens, n, pos0); if (rc) return rc;
     if (logits_last) NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));
     if (logits_last) memcpy(logits_last, m->h_logits, (size_t)m->c.vocab_size * 4);
+    return NL_OK;
+}
+
+int nl_bench_prefill(nl_model *m, const int32_t *tokens, int32_t n, int32_t pos0, float *ms_out, int32_t *launches_out) {
+    int rc = ready(m); if (rc) return rc;
+    if (!ms_out) return fail(NL_ERR_INVALID, "null argument");
+    rc = prefill_check(m, tokens, n, pos0); if (rc) return rc;
+    const bool gemm = prefill_gemm_ok(m, n);
+    if (gemm) { rc = ensure_pf(m); if (rc) return rc; }
+    m->pf_time = true;   // the prefill records ev0 after its token copy has landed
+    rc = gemm ? prefill_gemm(m, tokens, n, pos0) : prefill_sequential(m, tokens, n, pos0);
+    m->pf_time = false;
+    if (rc) return rc;
+    NL_CUDA(cudaEventRecord(m->ev1, m->st));
+    NL_CUDA(cudaStreamSynchronize(m->st));
+    NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
+    if (launches_out) *launches_out = m->pf_launches;
     return NL_OK;
 }
 

@@ -59,6 +59,7 @@ class LlamaModel:
         self.gamma = None
         self.max_batch = max_batch
         self.has_bias = has_bias
+        self.launches_last_prefill = 0
 
     # -- (*LlamaModel).Forward: no return value; OOB token/pos is a panic in Go -> IndexError here
     def forward(self, token: int, pos: int) -> None:
@@ -133,6 +134,14 @@ class LlamaModel:
     def bench_decode(self, token: int, pos0: int, n_steps: int) -> float:
         ms = C.c_float(0)
         capi.check(capi.lib().nl_bench_decode(self._h, int(token), int(pos0), int(n_steps), C.byref(ms)))
+        return ms.value
+
+    def bench_prefill(self, tokens: Sequence[int], pos0: int = 0) -> float:
+        """CUDA-event time (ms) of the prefill's kernels, prompt already on the device (nl_bench_prefill)."""
+        t = np.ascontiguousarray(tokens, dtype=np.int32)
+        ms, nl = C.c_float(0), C.c_int32(0)
+        capi.check(capi.lib().nl_bench_prefill(self._h, capi.ptr(t), t.size, int(pos0), C.byref(ms), C.byref(nl)))
+        self.launches_last_prefill = int(nl.value)
         return ms.value
 
     @property

@@ -69,6 +69,22 @@ def test_dequant_random_bytes_bit_exact_vs_oracle(typ):
     assert np.array_equal(got, exp)
 
 
+@pytest.mark.parametrize("key,typ", [("q5_0", G.GGML_Q5_0), ("q4_k", G.GGML_Q4_K), ("q6_k", G.GGML_Q6_K)])
+def test_kquant_dequant_and_matmul_vs_gguf_py_kat(golden_dir, key, typ):
+    """Q5_0 / Q4_K / Q6_K (go/quant.go:171-484) against the gguf-py known answers (tests/golden/make_kquant_kat.py): dequant bit for
+    bit, matmul against a float64 dot with the decoded weights and against the oracle."""
+    kq = np.load(os.path.join(golden_dir, "kquant_kat.npz"))
+    raw, exp = kq[key + "_bytes"], kq[key + "_expect"]
+    assert np.array_equal(M.dequant(typ, raw, exp.size).view(np.uint32), exp)
+    cols = 1024
+    rows = exp.size // cols
+    x = np.random.default_rng(7).standard_normal(cols).astype(np.float32)
+    got = M.matmul_dispatch(raw, typ, x, rows, cols)
+    ref = exp.view(np.float32).reshape(rows, cols).astype(np.float64) @ x.astype(np.float64)
+    assert np.abs(got - ref).max() / np.abs(ref).max() < 1e-5
+    assert maxrel(got, O.matmul(raw, typ, x, rows, cols)) < 1e-5
+
+
 def test_dequant_unsupported_type():
     with pytest.raises(Exception, match="unsupported"):
         M.dequant(3, np.zeros(20, np.uint8), 32)
@@ -251,6 +267,105 @@ def test_tied_embeddings_fallback(golden_dir, gold):
     m.close()
 
 
+# ---------------------------------------------------------------- optional attention biases (go/model.go:244-262, :525-527, :591)
+@pytest.mark.parametrize("name,path", [("tiny_gqa_q4_0", "decode_tiled_kernel"), ("tiny_gqa_q8_0", "decode_tiled_kernel"), ("tiny_gqa_f16", None)])
+def test_bias_tensors_every_decode_path(golden_dir, gold, name, path):
+    """A model that carries all four bias tensors through the persistent tiled kernel (Q4_0 / Q8_0), the per-matrix chain (F16 and
+    NL_NO_TILED), the one-pass prefill and the device-side greedy loop -- logits against the oracle fed the same tensors."""
+    from tests.helpers import WithBias
+    gf = WithBias(G.load_gguf(os.path.join(golden_dir, name + ".gguf")), seed=3)
+    plain = O.OracleModel(gf.gf)
+    m = M.load_llama_model(gf)
+    assert m.has_bias and (path is None or m.decode_path == path)
+    o = O.OracleModel(gf)
+    toks = np.resize(gold["tokens"], 40)
+    moved = 0
+    for pos, t in enumerate(toks):
+        m.forward(int(t), pos)
+        exp = o.forward(int(t), pos)
+        assert maxrel(m.state.logits, exp) < 2e-5, pos
+        moved += int(maxrel(plain.forward(int(t), pos), exp) > 1e-3)
+    assert moved >= 30          # the biases really change the logits
+    last = exp.copy()
+    m.reset()
+    m.prefill(toks)             # 40 tokens: the tcgen05 GEMM path with bias epilogues
+    assert maxrel(m.state.logits, last) < 1e-4
+    exp_s, margins = o.generate_greedy(toks[:8], 40)
+    got_s = m.generate_greedy(toks[:8], 40)
+    bad = [i for i in range(len(exp_s)) if got_s[i] != exp_s[i]]
+    assert len(got_s) == len(exp_s) and (not bad or margins[bad[0]] < 1e-5)
+    m.close()
+
+
+def test_bias_subset_and_chain_path(golden_dir, gold):
+    """Only some of the bias tensors present (each is optional on its own), on the per-matrix chain (NL_NO_TILED=1 in a fresh process)."""
+    import subprocess
+    import sys
+    root = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+    code = (
+        "import os, sys, numpy as np\n"
+        "sys.path.insert(0, %r)\n"
+        "from nanollama_b200 import gguf as G, model as M\n"
+        "from oracle import oracle as O\n"
+        "from tests.helpers import WithBias\n"
+        "gold = np.load(os.path.join(%r, 'golden_logits.npz'))\n"
+        "for which in (('attn_q', 'attn_output'), ('attn_k', 'attn_v'), ('attn_q', 'attn_k', 'attn_v', 'attn_output')):\n"
+        "    gf = WithBias(G.load_gguf(os.path.join(%r, 'tiny_gqa_q4_0.gguf')), seed=5, which=which)\n"
+        "    m = M.load_llama_model(gf); o = O.OracleModel(gf)\n"
+        "    assert m.decode_path == os.environ['EXPECT_PATH'], m.decode_path\n"
+        "    for pos, t in enumerate(gold['tokens']):\n"
+        "        m.forward(int(t), pos); exp = o.forward(int(t), pos)\n"
+        "        assert np.abs(m.state.logits - exp).max() / np.abs(exp).max() < 2e-5, (which, pos)\n"
+        "    m.close()\n"
+        "print('BIAS_OK')\n") % (root, golden_dir, golden_dir)
+    for env in ({"NL_NO_TILED": "1", "EXPECT_PATH": "gemv_stream_kernel chain"}, {"EXPECT_PATH": "decode_tiled_kernel"},
+                {"NL_TILE_POLL": "0", "EXPECT_PATH": "decode_tiled_kernel"}):
+        r = subprocess.run([sys.executable, "-c", code], env=dict(os.environ, **env), capture_output=True, text=True, timeout=600)
+        assert r.returncode == 0 and "BIAS_OK" in r.stdout, (env, r.stdout[-1500:], r.stderr[-1500:])
+
+
+def test_mixed_tensor_types_gate_up_differ(golden_dir, gold):
+    """gate in Q4_0, up in Q8_0, one projection downgraded to F16 (scripts/export_gguf.py:600-602): the per-matrix chain with the
+    unfused SwiGLU -- every GEMV must see the normed input (the up projection read a scratch buffer nobody wrote)."""
+    from tests.helpers import Retyped
+    base = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q4_0.gguf"))
+    gf = Retyped(base, {"blk.0.ffn_up.weight": G.GGML_Q8_0, "blk.1.ffn_up.weight": G.GGML_Q8_0, "blk.1.attn_k.weight": G.GGML_F16})
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    for pos, t in enumerate(gold["tokens"]):
+        m.forward(int(t), pos)
+        assert maxrel(m.state.logits, o.forward(int(t), pos)) < 2e-5, pos
+    m.close()
+
+
+def test_set_gamma_then_generate_without_a_forward(golden_dir, gold):
+    """nl_set_gamma drops the captured graphs; the greedy loop, the sequential prefill and the bench loop launch them directly
+    (ADVICE r1): they must have been re-captured."""
+    gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rows = (0.05 * np.random.default_rng(3).standard_normal((2, 128))).astype(np.float32)
+    mp = np.full(256, -1, np.int32)
+    prompt = gold["tokens"][:8]
+    mp[int(prompt[1])] = 0; mp[int(prompt[3])] = 1
+    m.set_gamma(rows, mp); o.set_gamma(rows, mp)
+    got = m.generate_greedy(prompt, 24)             # no forward in between
+    exp, margins = o.generate_greedy(prompt, 24)
+    bad = [i for i in range(24) if got[i] != exp[i]]
+    assert not bad or margins[bad[0]] < 1e-5
+    m.set_gamma(None, None)
+    m.prefill(prompt)                               # sequential prefill (< 16 tokens) right after dropping gamma
+    plain = O.OracleModel(gf)
+    for pos, t in enumerate(prompt):
+        e2 = plain.forward(int(t), pos)
+    assert maxrel(m.state.logits, e2) < 2e-5
+    assert m.bench_decode(int(prompt[0]), 0, 4) > 0
+    bad_map = mp.copy(); bad_map[5] = 7             # row index outside the table: rejected, not an out-of-bounds read
+    with pytest.raises(Exception):
+        m.set_gamma(rows, bad_map)
+    m.close()
+
+
 def test_batch_forward_matches_single(golden_dir, gold):
     gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q4_0.gguf"))
     m1 = M.load_llama_model(gf)
@@ -361,6 +476,85 @@ def test_wide_tier_logits_vs_oracle(tier, layers, vocab):
     for pos, t in enumerate(toks):
         m.forward(int(t), pos)
     assert np.array_equal(last, m.state.logits)
+    m.close(); o.close()
+
+
+@pytest.mark.parametrize("tier", ["big", "goldie"])
+def test_full_depth_benchmarked_config_vs_oracle(tier):
+    """The EXACT model bench.py times (big: 40 layers, 4096 wide, 96000 vocabulary, Q4_0 -- BASELINE configs 4 and 3 at full depth):
+    logits against the oracle at three prompt positions, 32 greedy steps fed the oracle's token (argmax identical unless the
+    oracle's own top-1 / top-2 margin is a rounding tie), and the device-side greedy loop against the same stream."""
+    import bench
+    gf = T.SyntheticGGUF(tier, G.GGML_Q4_0, seed=0, seq_len=min(2048, bench.PROMPT_LEN + 256 + 8))
+    m = M.load_llama_model(gf)
+    assert m.decode_path == "decode_tiled_kernel"
+    o = O.OracleModel(gf)
+    prompt = bench.bench_prompt(gf.meta.vocab_size)
+    worst = 0.0
+    for pos, t in enumerate(prompt):
+        exp = o.forward(int(t), pos)
+        m.forward(int(t), pos)
+        if pos in (0, 7, len(prompt) - 1):
+            worst = max(worst, maxrel(m.state.logits, exp))
+            assert maxrel(m.state.logits, exp) < 2e-5, pos
+    stream, pos = [], len(prompt)
+    for i in range(32):
+        srt = np.sort(exp)
+        margin = float((srt[-1] - srt[-2]) / max(abs(srt[-1]), 1e-30))
+        tok = int(np.argmax(exp))
+        assert int(np.argmax(m.state.logits)) == tok or margin < 1e-4, (i, margin)
+        stream.append(tok)
+        exp = o.forward(tok, pos)
+        m.forward(tok, pos)
+        assert maxrel(m.state.logits, exp) < LOGIT_TOL, i
+        worst = max(worst, maxrel(m.state.logits, exp))
+        pos += 1
+    got = m.generate_greedy(prompt, 32)
+    bad = [i for i in range(32) if got[i] != stream[i]]
+    assert not bad, bad[:3]
+    assert worst < 1e-4, worst
+    m.close(); o.close()
+
+
+def test_attention_to_the_end_of_the_context_vs_oracle():
+    """Positions 1023 / 1024 / 2046 of the 2048-position context cap (go/model.go:145): up to 16 attention splits per kv head whose
+    partials are folded across CTAs, second and third passes per split -- against the oracle; then the 2047-token one-pass prefill
+    (the most the engine ever feeds, go/main.go:163) against the oracle's logits at the last position."""
+    gf = T.SyntheticGGUF("mini", G.GGML_Q4_0, seed=2, seq_len=2048, vocab=2048, layers=4)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(4)
+    seq = rng.integers(3, 2048, size=2047).astype(np.int32)
+    for pos, t in enumerate(seq):
+        exp = o.forward(int(t), pos)
+        m.forward(int(t), pos)
+        if pos in (511, 1023, 1024, 1535, 2046):
+            assert maxrel(m.state.logits, exp) < 2e-5, pos
+            assert int(np.argmax(m.state.logits)) == int(np.argmax(exp)), pos
+    last = exp.copy()
+    with pytest.raises(IndexError):
+        m.forward(1, 2048)
+    m.reset()
+    m.prefill(seq)
+    assert maxrel(m.state.logits, last) < 1e-4
+    m.close(); o.close()
+
+
+def test_prefill_goldie_2047_tokens_vs_oracle():
+    """BASELINE config 3's prefill length on goldie's width (2 layers to keep the CPU side short): last-position logits vs the oracle,
+    then decode continues from the prefilled cache."""
+    gf = T.SyntheticGGUF("goldie", G.GGML_Q4_0, seed=6, seq_len=2048, vocab=4096, layers=2)
+    m = M.load_llama_model(gf)
+    o = O.OracleModel(gf)
+    rng = np.random.default_rng(8)
+    seq = np.concatenate([[1], rng.integers(3, 4096, size=2046)]).astype(np.int32)
+    for pos, t in enumerate(seq):
+        exp = o.forward(int(t), pos)
+    m.prefill(seq)
+    assert maxrel(m.state.logits, exp) < 1e-4
+    nxt = int(np.argmax(exp))
+    m.forward(nxt, 2047)
+    assert maxrel(m.state.logits, o.forward(nxt, 2047)) < 1e-4
     m.close(); o.close()
 
 

@@ -35,6 +35,35 @@ def test_dequant_bit_exact_vs_reference_bytes(kat, key, typ):
     assert np.array_equal(got, kat[key + "_expect"])
 
 
+KQ = [("q5_0", G.GGML_Q5_0), ("q4_k", G.GGML_Q4_K), ("q6_k", G.GGML_Q6_K)]
+
+
+@pytest.fixture(scope="module")
+def kq(golden_dir):
+    return np.load(os.path.join(golden_dir, "kquant_kat.npz"))
+
+
+@pytest.mark.parametrize("key,typ", KQ)
+def test_kquant_dequant_bit_exact_vs_gguf_py(kq, key, typ):
+    """DequantQ5_0 / DequantQ4_K / DequantQ6_K (go/quant.go:171-484) against gguf-py's independent decoder
+    (tests/golden/make_kquant_kat.py): every value, bit for bit."""
+    exp = kq[key + "_expect"]
+    got = O.dequant(typ, kq[key + "_bytes"], exp.size).view(np.uint32)
+    assert np.array_equal(got, exp)
+
+
+@pytest.mark.parametrize("key,typ", KQ)
+def test_kquant_matmul_vs_gguf_py_weights(kq, key, typ):
+    """MatMulQ5_0 / Q4_K / Q6_K: the oracle's product against a float64 dot with the gguf-py-decoded weights."""
+    w = kq[key + "_expect"].view(np.float32)
+    cols = 1024
+    rows = w.size // cols
+    x = np.random.default_rng(7).standard_normal(cols).astype(np.float32)
+    got = O.matmul(kq[key + "_bytes"], typ, x, rows, cols)
+    exp = w.reshape(rows, cols).astype(np.float64) @ x.astype(np.float64)
+    assert np.abs(got - exp).max() / np.abs(exp).max() < 1e-5
+
+
 def test_matmul_equals_dequant_then_dot_ordering(kat):
     # MatMulQ4_0 applies the scale after the per-block dot (go/quant.go:83-90); check against an explicit restatement
     rng = np.random.default_rng(0)
