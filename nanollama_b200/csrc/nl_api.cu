@@ -279,6 +279,10 @@ struct nl_model {
     float2 *amax = nullptr; bool amax_valid = false;   // per-CTA argmax pairs of the LM-head phase
     float *qkv_bias = nullptr;
     TilePhase *d_tphases = nullptr; TileArgs targs; int tile_grid = 0;
+    // tensor parallel + polled: one arena per token parity inside the window, a descriptor list / TileArgs / graph pair per parity, strictly
+    // alternated by the host (every rank launches the same sequence of forwards)
+    TpArena tp_arena{}; bool tp_poll = false; TileArgs targs1; int tok_parity = 0; int *d_lg_want = nullptr; unsigned int *d_pf_epoch = nullptr;
+    cudaGraphExec_t g_fwd_odd = nullptr, g_step_odd = nullptr;
 };
 
 static int set_dev(const nl_model *m) {
@@ -372,82 +376,151 @@ static int build_tiled(nl_model *m) {
             if (ly.bv) NL_CUDA(cudaMemcpyAsync(b + qdim + kvd, ly.bv, (size_t)kvd * 4, cudaMemcpyDeviceToDevice, st));
         }
     }
-    std::vector<TilePhase> ph;
-    TilePhase P;
     int rc;
-    // Single GPU: polled single-use activation vectors, no grid barrier (nl_tile.cu, "polled activations"); per layer
-    // q|k|v, attention output, post-attention residual, SwiGLU output, layer output live in one arena that record_forward fills with
-    // the sentinel before every launch.  NL_TILE_POLL=0 (and tensor parallel): shared vectors behind release / acquire grid barriers.
-    const int POLL = (!tpar && !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0)) ? 1 : 0;
-    const size_t per_layer = (size_t)nqkv + qdim + dim + ffn + dim;
-    if (POLL) {
+    // Polled single-use activation vectors, no grid barrier (nl_tile.cu, "polled activations"): per layer q|k|v, attention output,
+    // post-attention residual, SwiGLU output, layer output live in one arena that record_forward fills with the sentinel before every
+    // launch.  Tensor parallel: the arena sits in the IPC window (the peers store their partials of the row-split products into it),
+    // one per token parity (nl_tp.cuh, TpArena).  NL_TILE_POLL=0: shared vectors behind release / acquire grid barriers.
+    const int POLL = !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0) ? 1 : 0;
+    // producer-side fragments (nl_tile.cuh): every vector a GEMV reads is published by its producer as that GEMV's fragment image,
+    // behind the fp32 copy where the residual path still needs one.  NL_TILE_IMG=0: fp32 vectors only, converted by every consumer.
+    const int IMG = (POLL && !(getenv("NL_TILE_IMG") && atoi(getenv("NL_TILE_IMG")) == 0)) ? 1 : 0;
+    const bool tpoll = tpar && POLL;
+    if (tpoll && !IMG) return fail(NL_ERR_UNSUPPORTED, "the polled tensor-parallel path needs the fragment images (unset NL_TILE_IMG=0 or set NL_TILE_POLL=0)");
+    // single GPU, per layer (floats): q|k|v, attention output, post-attention residual, SwiGLU output, layer output; then (IMG) the
+    // images of the attention output, the post-attention residual, the SwiGLU output and the layer output
+    const size_t f_qkv = 0, f_ao = f_qkv + nqkv, f_xres = f_ao + (IMG ? 0 : qdim), f_hb = f_xres + dim, f_xout = f_hb + (IMG ? 0 : ffn);
+    const size_t i_ao = f_xout + dim, i_xres = i_ao + (IMG ? tile_img_bytes(qdim) / 4 : 0), i_hb = i_xres + (IMG ? tile_img_bytes(dim) / 4 : 0),
+                 i_xout = i_hb + (IMG ? tile_img_bytes(ffn) / 4 : 0), per_layer = i_xout + (IMG ? tile_img_bytes(dim) / 4 : 0);
+    if (POLL && !tpar) {
         m->arena_bytes = (size_t)c.n_layers * per_layer * 4;
         NL_CUDA(cudaMalloc(&m->arena, m->arena_bytes));
         NL_CUDA(cudaMemset(m->arena, 0xFF, m->arena_bytes));
     }
-    void *xres = (void *)m->x;
-    // tensor parallel: exchange e (o-projection of layer l: e = 2l, down-projection: e = 2l + 1) uses parity e & 1 of the exchange area;
-    // its consumer adds the ranks' partials to the residual before it (the embedding for e = 0, else xres2[(e - 1) & 1]) and leaves
-    // the sum in xres2[e & 1]
+    if (tpoll) {
+        if (m->tp_arena.total == 0 || m->tp_lay.arena[1] + m->tp_arena.total > m->tp_lay.total) return fail(NL_ERR_STATE, "internal: tensor-parallel arena not laid out");
+        NL_CUDA(cudaMemset(m->tp_win + m->tp_lay.arena[0], 0xFF, m->tp_arena.total));
+        NL_CUDA(cudaMemset(m->tp_win + m->tp_lay.arena[1], 0xFF, m->tp_arena.total));
+    }
+    for (int l = 0; l < c.n_layers; l++) {   // the tiled matrices: per layer qkv, o, gate/up, down; then the LM head
+        Layer &ly = m->L[l];
+        uint8_t *t = nullptr;
+        const DevMat *qkv[3] = {&ly.wq, &ly.wk, &ly.wv}, *o[1] = {&ly.wo}, *gu[2] = {&ly.wgate, &ly.wup}, *dn[1] = {&ly.wdown};
+        if ((rc = make_tiles(&t, qkv, 3, false, st))) return rc;
+        m->tile_bufs.push_back(t);
+        if ((rc = make_tiles(&t, o, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t);
+        if ((rc = make_tiles(&t, gu, 2, true, st))) return rc;
+        m->tile_bufs.push_back(t);
+        if ((rc = make_tiles(&t, dn, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t);
+    }
+    {
+        uint8_t *t = nullptr;
+        const DevMat *lm[1] = {&outw};
+        if ((rc = make_tiles(&t, lm, 1, false, st))) return rc;
+        m->tile_bufs.push_back(t);
+    }
+    // tensor parallel, barrier mode: exchange e (o-projection of layer l: e = 2l, down-projection: e = 2l + 1) uses parity e & 1 of the
+    // exchange area; its consumer adds the ranks' partials to the residual before it (the embedding for e = 0, else xres2[(e - 1) & 1])
+    // and leaves the sum in xres2[e & 1]
     float *xres2[2] = {reinterpret_cast<float *>(m->x_sh), reinterpret_cast<float *>(m->x_sh) + dim};   // 2 x dim floats fit the pair buffer
     auto consume_exchange = [&](TilePhase &Q, int e) {
         Q.in_exch = 1; Q.par = e & 1; Q.prev = e == 0 ? m->x : xres2[(e - 1) & 1]; Q.next = xres2[e & 1];
     };
-    for (int l = 0; l < c.n_layers; l++) {
-        Layer &ly = m->L[l];
-        uint8_t *t_qkv = nullptr, *t_o = nullptr, *t_gu = nullptr, *t_dn = nullptr;
-        const DevMat *qkv[3] = {&ly.wq, &ly.wk, &ly.wv}, *o[1] = {&ly.wo}, *gu[2] = {&ly.wgate, &ly.wup}, *dn[1] = {&ly.wdown};
-        if ((rc = make_tiles(&t_qkv, qkv, 3, false, st))) return rc;
-        m->tile_bufs.push_back(t_qkv);
-        if ((rc = make_tiles(&t_o, o, 1, false, st))) return rc;
-        m->tile_bufs.push_back(t_o);
-        if ((rc = make_tiles(&t_gu, gu, 2, true, st))) return rc;
-        m->tile_bufs.push_back(t_gu);
-        if ((rc = make_tiles(&t_dn, dn, 1, false, st))) return rc;
-        m->tile_bufs.push_back(t_dn);
-        // this layer's vectors: shared buffers, or (polled) its own slice of the arena; layer 0 reads the embedding kernel's plain x
-        float *a_l = POLL ? m->arena + (size_t)l * per_layer : nullptr;
-        void *qkv_l = POLL ? (void *)a_l : (void *)m->qkv_sh, *ao_l = POLL ? (void *)(a_l + nqkv) : (void *)m->ao_sh;
-        void *hb_l = POLL ? (void *)(a_l + nqkv + qdim + dim) : (void *)m->hb_sh;
-        const void *x_in = (l == 0 || !POLL) ? (const void *)m->x : (const void *)(a_l - dim);   // the layer before's output
-        if (POLL) xres = a_l + nqkv + qdim;            // post-attention residual (output of the o-projection)
-        void *x_out = POLL ? (void *)(a_l + nqkv + qdim + dim + ffn) : xres;
-        tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, POLL && l > 0, ly.attn_norm, m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr, qkv_l, POLL);
-        if (tpar && l > 0) consume_exchange(P, 2 * l - 1);
+    // one phase list; tensor parallel + polled: one per token parity `tok_par` (the descriptors carry that parity's arena addresses)
+    auto make_list = [&](int tok_par) -> std::vector<TilePhase> {
+        std::vector<TilePhase> ph;
+        TilePhase P;
+        void *xres = (void *)m->x;
+        const uint8_t *img_last = nullptr;
+        const TpArena &ta = m->tp_arena;
+        uint8_t *tbase = tpoll ? m->tp_win + m->tp_lay.arena[tok_par] : nullptr;
+        for (int l = 0; l < c.n_layers; l++) {
+            Layer &ly = m->L[l];
+            uint8_t *t_qkv = m->tile_bufs[4 * l], *t_o = m->tile_bufs[4 * l + 1], *t_gu = m->tile_bufs[4 * l + 2], *t_dn = m->tile_bufs[4 * l + 3];
+            const float *qb = m->qkv_bias ? m->qkv_bias + (size_t)l * nqkv : nullptr;
+            const float *next_norm = l + 1 < c.n_layers ? m->L[l + 1].attn_norm : m->output_norm;
+            if (tpoll) {
+                // polled exchange: the o / down finishing warps store this rank's partial into slot `rank` of every rank's part_o / part_d;
+                // the consumer of an exchange (gate/up, the next layer's qkv, the LM head) polls the residual before it and the tp
+                // partials, sums them in rank order (identical on every rank) and its first CTA leaves the new residual in xres / xout
+                uint8_t *al = tbase + (size_t)l * ta.per_layer, *ap = al - ta.per_layer;
+                const unsigned long long woff = m->tp_lay.arena[tok_par] + (size_t)l * ta.per_layer;
+                float *qkv_l = reinterpret_cast<float *>(al + ta.qkv);
+                tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, m->x, 0, ly.attn_norm, qb, qkv_l, 1);
+                if (l > 0) { P.in_exch = 1; P.prev = reinterpret_cast<const float *>(ap + ta.xres); P.prev_poll = 1; P.parts = reinterpret_cast<const float *>(ap + ta.part_d);
+                             P.next = reinterpret_cast<float *>(ap + ta.xout); }
+                ph.push_back(P);
+                memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; P.x = qkv_l; P.out = nullptr; P.out_img = al + ta.ao_img; ph.push_back(P);
+                tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, nullptr, 0, nullptr, ly.bo, nullptr, 0);
+                P.in_img = al + ta.ao_img; P.exch_out = 1; P.exch_off = woff + ta.part_o;
+                ph.push_back(P);
+                tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, nullptr, 0, ly.ffn_norm, nullptr, nullptr, 0);
+                P.in_exch = 1; P.prev = l == 0 ? m->x : reinterpret_cast<const float *>(ap + ta.xout); P.prev_poll = l > 0; P.parts = reinterpret_cast<const float *>(al + ta.part_o);
+                P.next = reinterpret_cast<float *>(al + ta.xres); P.out_img = al + ta.hb_img;
+                ph.push_back(P);
+                tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, nullptr, 0, nullptr, nullptr, nullptr, 0);
+                P.in_img = al + ta.hb_img; P.exch_out = 1; P.exch_off = woff + ta.part_d;
+                ph.push_back(P);
+                continue;
+            }
+            // this layer's vectors: shared buffers, or (polled) its own slice of the arena; layer 0 reads the embedding kernel's plain x
+            float *a_l = POLL ? m->arena + (size_t)l * per_layer : nullptr;
+            void *qkv_l = POLL ? (void *)(a_l + f_qkv) : (void *)m->qkv_sh, *ao_l = POLL ? (IMG ? nullptr : (void *)(a_l + f_ao)) : (void *)m->ao_sh;
+            void *hb_l = POLL ? (IMG ? nullptr : (void *)(a_l + f_hb)) : (void *)m->hb_sh;
+            const void *x_in = (l == 0 || !POLL) ? (const void *)m->x : (const void *)(a_l - per_layer + f_xout);   // the layer before's output
+            if (POLL) xres = a_l + f_xres;            // post-attention residual (output of the o-projection)
+            void *x_out = POLL ? (void *)(a_l + f_xout) : xres;
+            uint8_t *img_ao = IMG ? reinterpret_cast<uint8_t *>(a_l + i_ao) : nullptr, *img_xres = IMG ? reinterpret_cast<uint8_t *>(a_l + i_xres) : nullptr;
+            uint8_t *img_hb = IMG ? reinterpret_cast<uint8_t *>(a_l + i_hb) : nullptr, *img_xout = IMG ? reinterpret_cast<uint8_t *>(a_l + i_xout) : nullptr;
+            const uint8_t *img_xin = (IMG && l > 0) ? reinterpret_cast<const uint8_t *>(a_l - per_layer + i_xout) : nullptr;
+            tile_gemv_phase(P, t_qkv, nqkv / 16, dim, 1, nqkv, TEPI_STORE, x_in, POLL && l > 0, ly.attn_norm, qb, qkv_l, POLL);
+            P.in_img = img_xin;
+            if (tpar && l > 0) consume_exchange(P, 2 * l - 1);
+            ph.push_back(P);
+            memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; P.x = (const float *)qkv_l; P.out = (float *)ao_l; P.out_img = img_ao; ph.push_back(P);
+            if (tpar) {
+                tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, ao_l, 0, nullptr, ly.bo, nullptr, 0);
+                P.exch_out = 1; P.par = 0; P.cross = 1;
+            } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, ao_l, POLL, nullptr, ly.bo, xres, POLL, x_in, POLL && l > 0);
+            P.in_img = img_ao; P.out_img = img_xres; P.out_nw = IMG ? ly.ffn_norm : nullptr;
+            ph.push_back(P);
+            tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, POLL, ly.ffn_norm, nullptr, hb_l, POLL);
+            P.in_img = img_xres; P.out_img = img_hb;
+            if (tpar) consume_exchange(P, 2 * l);
+            ph.push_back(P);
+            if (tpar) {
+                tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, hb_l, 0, nullptr, nullptr, nullptr, 0);
+                P.exch_out = 1; P.par = 1; P.cross = 1;
+            } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, hb_l, POLL, nullptr, nullptr, x_out, POLL, xres, POLL);
+            P.in_img = img_hb; P.out_img = img_xout; P.out_nw = IMG ? next_norm : nullptr;
+            ph.push_back(P);
+            if (IMG) img_last = img_xout;
+            if (POLL) xres = x_out;   // what the next layer (or the LM head) reads
+        }
+        uint8_t *t_lm = m->tile_bufs[4 * (size_t)c.n_layers];
+        tile_gemv_phase(P, t_lm, lvocab / 16, dim, 1, lvocab, TEPI_STORE, xres, POLL && !tpar, m->output_norm, nullptr, m->logits, 0);
+        P.in_img = img_last;
+        if (tpoll) {
+            uint8_t *ap = tbase + (size_t)(c.n_layers - 1) * ta.per_layer;
+            P.in_exch = 1; P.prev = reinterpret_cast<const float *>(ap + ta.xres); P.prev_poll = 1; P.parts = reinterpret_cast<const float *>(ap + ta.part_d);
+            P.next = reinterpret_cast<float *>(ap + ta.xout);
+        } else if (tpar) { consume_exchange(P, 2 * c.n_layers - 1); P.cross = 1; }   // vocab shard -> every rank's full logits vector
         ph.push_back(P);
-        memset(&P, 0, sizeof P); P.kind = PH_ATTN; P.layer = l; P.x = (const float *)qkv_l; P.out = (float *)ao_l; ph.push_back(P);
-        if (tpar) {
-            tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_STORE, ao_l, 0, nullptr, ly.bo, nullptr, 0);
-            P.exch_out = 1; P.par = 0; P.cross = 1;
-        } else tile_gemv_phase(P, t_o, dim / 16, qdim, 1, dim, TEPI_RESID, ao_l, POLL, nullptr, ly.bo, xres, POLL, x_in, POLL && l > 0);
-        ph.push_back(P);
-        tile_gemv_phase(P, t_gu, 2 * (ffn / 16), dim, 2, ffn, TEPI_SWIGLU, xres, POLL, ly.ffn_norm, nullptr, hb_l, POLL);
-        if (tpar) consume_exchange(P, 2 * l);
-        ph.push_back(P);
-        if (tpar) {
-            tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_STORE, hb_l, 0, nullptr, nullptr, nullptr, 0);
-            P.exch_out = 1; P.par = 1; P.cross = 1;
-        } else tile_gemv_phase(P, t_dn, dim / 16, ffn, 1, dim, TEPI_RESID, hb_l, POLL, nullptr, nullptr, x_out, POLL, xres, POLL);
-        ph.push_back(P);
-        if (POLL) xres = x_out;   // what the next layer (or the LM head) reads
-    }
-    {
-        uint8_t *t_lm = nullptr;
-        const DevMat *lm[1] = {&outw};
-        if ((rc = make_tiles(&t_lm, lm, 1, false, st))) return rc;
-        m->tile_bufs.push_back(t_lm);
-        tile_gemv_phase(P, t_lm, lvocab / 16, dim, 1, lvocab, TEPI_STORE, xres, POLL, m->output_norm, nullptr, m->logits, 0);
-        if (tpar) { consume_exchange(P, 2 * c.n_layers - 1); P.cross = 1; }   // vocab shard -> every rank's full logits vector
-        ph.push_back(P);
-    }
-    for (size_t i = 1; i < ph.size(); i++) ph[i].wait_cross = ph[i - 1].cross;
+        for (size_t i = 1; i < ph.size(); i++) ph[i].wait_cross = ph[i - 1].cross;
+        return ph;
+    };
+    std::vector<TilePhase> ph = make_list(0);
+    if (tpoll) { std::vector<TilePhase> ph1 = make_list(1); ph.insert(ph.end(), ph1.begin(), ph1.end()); }
+    const size_t n_ph = tpoll ? ph.size() / 2 : ph.size();
     NL_CUDA(cudaStreamSynchronize(st));
     int nsplit = G / m->nKV;
     if (nsplit < 1) nsplit = 1;
     if (nsplit > MG_MAX_SPLIT) nsplit = MG_MAX_SPLIT;
     NL_CUDA(cudaMalloc(&m->d_tphases, ph.size() * sizeof(TilePhase)));
     NL_CUDA(cudaMemcpy(m->d_tphases, ph.data(), ph.size() * sizeof(TilePhase), cudaMemcpyHostToDevice));
-    const size_t n_cnt = ph.size() + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
+    const size_t n_cnt = n_ph + (size_t)c.n_layers * c.n_kv_heads;   // phase barriers, then per-(layer, kv head) split counters
     NL_CUDA(cudaMalloc(&m->d_bar, n_cnt * sizeof(unsigned int)));
     NL_CUDA(cudaMalloc(&m->part_acc, (size_t)m->nH * nsplit * 64 * 8));   // flagged pairs
     NL_CUDA(cudaMalloc(&m->part_ml, (size_t)m->nH * nsplit * 2 * 8));
@@ -455,8 +528,9 @@ static int build_tiled(nl_model *m) {
     NL_CUDA(cudaMemset(m->part_ml, 0, (size_t)m->nH * nsplit * 2 * 8));
     TileArgs &a = m->targs;
     memset(&a, 0, sizeof a);
-    a.phases = m->d_tphases; a.n_phases = (int)ph.size(); a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = POLL;
+    a.phases = m->d_tphases; a.n_phases = (int)n_ph; a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = POLL;
     a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.att_hpi = tile_env_int("NL_ATT_HPI", 0, 0, 64); a.amax = m->amax; m->amax_valid = true;
+    a.dbg = tile_env_int("NL_TILE_DBG", 0, 0, 3);
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_sh); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
@@ -465,16 +539,24 @@ static int build_tiled(nl_model *m) {
         a.tp = m->tp; a.rank = m->rank; a.dim = dim; a.lvocab = lvocab; a.peers = m->tp_peers;
         a.ar_off = m->tp_lay.ar_data; a.bar_off = m->tp_lay.tile_bar; a.lg_off = m->tp_lay.lg_data; a.amax_off = m->tp_lay.tile_amax;
         a.bar = reinterpret_cast<unsigned int *>(m->tp_win + m->tp_lay.tile_bar);
+        a.lg_want = m->d_lg_want;
     }
     a.at.nsplit = nsplit; a.at.out = reinterpret_cast<float *>(m->ao_sh); a.at.eps = c.rms_norm_eps;
     a.at.scale = (float)(1.0 / sqrt((double)m->hd));
     if (getenv("NL_TRACE")) {  // latency forensics: per-CTA, per-phase globaltimer stamps of the last token (dumped by nl_bench_decode)
-        NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
-        NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * ph.size() * 8 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMalloc(&m->d_trace, (size_t)G * n_ph * 8 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMemset(m->d_trace, 0, (size_t)G * n_ph * 8 * sizeof(unsigned long long)));
         a.trace = m->d_trace;
-        NL_CUDA(cudaMalloc(&m->d_trace2, (size_t)G * ph.size() * 16 * sizeof(unsigned long long)));
-        NL_CUDA(cudaMemset(m->d_trace2, 0, (size_t)G * ph.size() * 16 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMalloc(&m->d_trace2, (size_t)G * n_ph * 16 * sizeof(unsigned long long)));
+        NL_CUDA(cudaMemset(m->d_trace2, 0, (size_t)G * n_ph * 16 * sizeof(unsigned long long)));
         a.trace2 = m->d_trace2;
+    }
+    m->tp_poll = tpoll;
+    if (tpoll) {   // parity 1: its own descriptor list and argmax-pair area; the host alternates the two (tile_args_for)
+        m->targs.amax_off = m->tp_lay.arena[0] + m->tp_arena.amax;
+        m->targs1 = m->targs;
+        m->targs1.phases = m->d_tphases + n_ph;
+        m->targs1.amax_off = m->tp_lay.arena[1] + m->tp_arena.amax;
     }
     m->tile_grid = G; m->tile_type = wtype;
     m->tile_ok = true;
@@ -485,7 +567,7 @@ static bool batch_gemm_ok(const nl_model *m, int batch);
 static int record_forward_batch_gemm(nl_model *m, int batch);
 
 // The launch sequence of one Forward for `batch` sequences (go/model.go:490-620).  Recorded into a CUDA graph.
-static int record_forward(nl_model *m, int batch) {
+static int record_forward(nl_model *m, int batch, int par = 0) {
     const nl_config &c = m->c;
     cudaStream_t st = m->st;
     const int dim = m->dim, hd = m->hd, kvd = m->kvd, qdim = m->qdim, S = c.seq_len, ffn = m->ffn;   // shard sizes when tp > 1
@@ -501,11 +583,14 @@ static int record_forward(nl_model *m, int batch) {
         // everything after the embedding in ONE persistent tensor-core kernel (nl_tile.cuh); its grid-barrier counters start at zero
         // (tensor parallel: the counters live in the IPC window and are never reset)
         // (polled activations: no barriers; every activation vector of the token starts out as sentinels instead)
-        if (m->targs.poll) NL_CUDA(cudaMemsetAsync(m->arena, 0xFF, m->arena_bytes, st));
+        // (tensor parallel + polled: this token runs in arena `par`; the OTHER one is refilled for the next token -- no peer writes it
+        // before every rank has finished this token, and everything it held was consumed by the token before, nl_tp.cuh)
+        if (m->tp_poll) NL_CUDA(cudaMemsetAsync(m->tp_win + m->tp_lay.arena[par ^ 1], 0xFF, m->tp_arena.total, st));
+        else if (m->targs.poll) NL_CUDA(cudaMemsetAsync(m->arena, 0xFF, m->arena_bytes, st));
         else if (m->tp == 1) NL_CUDA(cudaMemsetAsync(m->d_bar, 0, ((size_t)m->targs.n_phases + (size_t)m->c.n_layers * m->c.n_kv_heads) * sizeof(unsigned int), st));
         bump_epoch_kernel<<<1, 1, 0, st>>>(m->d_epoch);   // new flags for this token's activation vectors
         launches++;
-        if (launch_tiled(m->tile_type, m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+        if (launch_tiled(m->tile_type, par ? m->targs1 : m->targs, m->tile_grid, st)) return fail(NL_ERR_CUDA, "tiled decode kernel launch failed: %s", cudaGetErrorString(cudaGetLastError()));
         launches++;
         NL_CUDA(cudaGetLastError());
         m->launches_fwd = launches;
@@ -584,11 +669,13 @@ static int ensure_pf(nl_model *m) {
     // sized once for the longest prompt and the largest batch: captured graphs keep these pointers
     const int rows = m->B > m->c.seq_len ? m->B : m->c.seq_len;
     if (m->pf_cap >= rows) return NL_OK;
-    if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); m->pf_cap = 0; }
+    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); m->pf_cap = 0; }
     const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, ld = qdim + 2 * kvd;
     const size_t T = (size_t)rows;
     size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
-    NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4)); NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
+    if (m->tp > 1) m->pf_x = reinterpret_cast<float *>(m->tp_win + m->tp_lay.pf_x);   // tensor parallel: the residual rows live in the window (nl_tp.cuh)
+    else NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4));
+    NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
     NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
     NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
     m->pf_cap = rows;
@@ -658,11 +745,13 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
     return NL_OK;
 }
 
-static int record_advance(nl_model *m, int batch) {
+static int record_advance(nl_model *m, int batch, int par = 0) {
     StepState s{m->d_token, m->d_pos, m->d_gen, m->d_gen_count, m->gen_cap};
     // batch 1 on the tiled path: the LM-head phase of the previous forward left one (max, index) pair per CTA
+    // (tensor parallel + polled: the previous token ran in the other parity's arena)
     if (batch == 1 && m->tile_ok && m->amax_valid) {
-        const float2 *pairs = m->tp > 1 ? reinterpret_cast<const float2 *>(m->tp_win + m->tp_lay.tile_amax) : m->amax;
+        const float2 *pairs = m->tp_poll ? reinterpret_cast<const float2 *>(m->tp_win + m->tp_lay.arena[par ^ 1] + m->tp_arena.amax)
+                            : m->tp > 1 ? reinterpret_cast<const float2 *>(m->tp_win + m->tp_lay.tile_amax) : m->amax;
         argmax_pairs_advance_kernel<<<1, 32, 0, m->st>>>(pairs, m->tile_grid * m->tp, s);
     }
     else argmax_advance_kernel<<<batch, 1024, 0, m->st>>>(m->logits, m->c.vocab_size, s);
@@ -691,6 +780,36 @@ static int build_graphs(nl_model *m, int batch) {
     NL_CUDA(e);
     NL_CUDA(cudaGraphInstantiate(&m->g_step[batch], g, 0));
     cudaGraphDestroy(g);
+    if (m->tp_poll && batch == 1) {   // the odd-parity twins
+        NL_CUDA(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
+        rc = record_forward(m, 1, 1);
+        e = cudaStreamEndCapture(m->st, &g);
+        if (rc) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+        NL_CUDA(e);
+        NL_CUDA(cudaGraphInstantiate(&m->g_fwd_odd, g, 0));
+        cudaGraphDestroy(g);
+        NL_CUDA(cudaStreamBeginCapture(m->st, cudaStreamCaptureModeThreadLocal));
+        rc = record_advance(m, 1, 1);
+        if (!rc) rc = record_forward(m, 1, 1);
+        e = cudaStreamEndCapture(m->st, &g);
+        if (rc) { if (e == cudaSuccess) cudaGraphDestroy(g); return rc; }
+        NL_CUDA(e);
+        NL_CUDA(cudaGraphInstantiate(&m->g_step_odd, g, 0));
+        cudaGraphDestroy(g);
+    }
+    return NL_OK;
+}
+// The graph of the next batch-1 forward (step = argmax / advance first).  Tensor parallel + polled: the two parities alternate.
+static cudaGraphExec_t next_graph(nl_model *m, bool step) {
+    if (!m->tp_poll) return step ? m->g_step[1] : m->g_fwd[1];
+    const int par = m->tok_parity;
+    m->tok_parity ^= 1;
+    return step ? (par ? m->g_step_odd : m->g_step[1]) : (par ? m->g_fwd_odd : m->g_fwd[1]);
+}
+// tensor parallel: does the next forward's LM head spread its logits shard over the peers' windows (the caller reads logits), or only
+// the argmax pairs (greedy / bench loops)?
+static int set_lg_want(nl_model *m, int want) {
+    if (m->d_lg_want) NL_CUDA(cudaMemsetAsync(m->d_lg_want, want ? 1 : 0, 4, m->st));
     return NL_OK;
 }
 
@@ -839,6 +958,8 @@ int nl_set_gamma(nl_model *m, const float *rows, int32_t n_rows, const int32_t *
     NL_CUDA(cudaStreamSynchronize(m->st));
     for (auto &g : m->g_fwd) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
     for (auto &g : m->g_step) if (g) { cudaGraphExecDestroy(g); g = nullptr; }
+    if (m->g_fwd_odd) { cudaGraphExecDestroy(m->g_fwd_odd); m->g_fwd_odd = nullptr; }
+    if (m->g_step_odd) { cudaGraphExecDestroy(m->g_step_odd); m->g_step_odd = nullptr; }
     if (m->gamma) { cudaFree(m->gamma); m->gamma = nullptr; }
     if (m->gamma_map) { cudaFree(m->gamma_map); m->gamma_map = nullptr; }
     if (rows) {
@@ -903,9 +1024,14 @@ int nl_finalize(nl_model *m) {
     if (S * sizeof(float) > 48 * 1024) return fail(NL_ERR_INVALID, "seq_len too large for the attention kernel");
     if (m->tp > 1) {
         // exchange window (exported to the peers with CUDA IPC), partial-product buffer, local logits shard
-        m->tp_lay = tp_layout(m->tp, dim, c.vocab_size);
+        m->tp_arena = tp_arena(m->tp, dim, qdim + 2 * kvd, tile_img_bytes(qdim), tile_img_bytes(ffn), c.n_layers);
+        m->tp_lay = tp_layout(m->tp, dim, c.vocab_size, m->tp_arena.total, c.seq_len);
         NL_CUDA(cudaMalloc(&m->tp_win, m->tp_lay.total));
         NL_CUDA(cudaMemset(m->tp_win, 0, m->tp_lay.total));
+        NL_CUDA(cudaMalloc(&m->d_lg_want, 4));
+        NL_CUDA(cudaMemset(m->d_lg_want, 1, 4));
+        NL_CUDA(cudaMalloc(&m->d_pf_epoch, 4));
+        NL_CUDA(cudaMemset(m->d_pf_epoch, 0, 4));
         m->logits = reinterpret_cast<float *>(m->tp_win + m->tp_lay.lg_data);
         if ((rc = alloc(&m->partial, (size_t)dim)) || (rc = alloc(&m->logits_local, (size_t)m->lvocab))) return rc;
         NL_CUDA(cudaMalloc(&m->d_ar_epoch, 4)); NL_CUDA(cudaMalloc(&m->d_lg_epoch, 4));
@@ -939,6 +1065,10 @@ void nl_destroy(nl_model *m) {
     if (m->st) cudaStreamSynchronize(m->st);
     for (auto g : m->g_fwd) if (g) cudaGraphExecDestroy(g);
     for (auto g : m->g_step) if (g) cudaGraphExecDestroy(g);
+    if (m->g_fwd_odd) cudaGraphExecDestroy(m->g_fwd_odd);
+    if (m->g_step_odd) cudaGraphExecDestroy(m->g_step_odd);
+    if (m->d_lg_want) cudaFree(m->d_lg_want);
+    if (m->d_pf_epoch) cudaFree(m->d_pf_epoch);
     free_mat(m->tok_embd); free_mat(m->output);
     for (auto &ly : m->L) {
         free_mat(ly.wq); free_mat(ly.wk); free_mat(ly.wv); free_mat(ly.wo); free_mat(ly.wgate); free_mat(ly.wup); free_mat(ly.wdown);
@@ -959,7 +1089,7 @@ void nl_destroy(nl_model *m) {
     }
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->d_trace2) cudaFree(m->d_trace2);
-    if (m->pf_cap) { cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
+    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
     for (void *q : {(void *)m->x_sh, (void *)m->qkv_sh, (void *)m->ao_sh, (void *)m->hb_sh, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
@@ -997,7 +1127,7 @@ int nl_forward_batch(nl_model *m, int32_t B, const int32_t *tokens, const int32_
     memcpy(m->h_stage, tokens, B * 4); memcpy(m->h_stage + 64, pos, B * 4);
     NL_CUDA(cudaMemcpyAsync(m->d_token, m->h_stage, B * 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + 64, B * 4, cudaMemcpyHostToDevice, m->st));
-    NL_CUDA(cudaGraphLaunch(m->g_fwd[B], m->st));
+    NL_CUDA(cudaGraphLaunch(B == 1 ? next_graph(m, false) : m->g_fwd[B], m->st));
     if (logits_out) NL_CUDA(cudaMemcpyAsync(m->h_logits, m->logits, (size_t)B * m->c.vocab_size * 4, cudaMemcpyDeviceToHost, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));
     if (logits_out) memcpy(logits_out, m->h_logits, (size_t)B * m->c.vocab_size * 4);
@@ -1062,9 +1192,11 @@ static int prefill_sequential(nl_model *m, const int32_t *tokens, int n, int pos
     NL_CUDA(cudaMemsetAsync(m->d_cursor, 0, 4, m->st));
     NL_CUDA(cudaStreamSynchronize(m->st));  // tokens is caller memory: the copy must be done before we return or reuse it
     if (m->pf_time) NL_CUDA(cudaEventRecord(m->ev0, m->st));
+    if (n > 1) { int rcw = set_lg_want(m, 0); if (rcw) return rcw; }   // only the last token's logits are ever read
     for (int i = 0; i < n; i++) {
+        if (i == n - 1 && n > 1) { int rcw = set_lg_want(m, 1); if (rcw) return rcw; }
         feed_prompt_kernel<<<1, 1, 0, m->st>>>(m->d_prompt, m->d_cursor, pos0, m->d_token, m->d_pos);
-        NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
+        NL_CUDA(cudaGraphLaunch(next_graph(m, false), m->st));
     }
     m->pf_launches = n * (m->launches_fwd + 1);
     NL_CUDA(cudaGetLastError());
@@ -1073,7 +1205,8 @@ static int prefill_sequential(nl_model *m, const int32_t *tokens, int n, int pos
 
 // One-pass prefill on the tensor cores: every projection of the T prompt tokens is ONE tcgen05 GEMM (nl_gemm.cuh) instead of T GEMVs.
 static bool prefill_gemm_ok(const nl_model *m, int n) {
-    if (getenv("NL_NO_GEMM_PREFILL") || n < 16 || m->tp > 1 || m->hd != 64) return false;
+    if (getenv("NL_NO_GEMM_PREFILL") || n < 16 || m->hd != 64) return false;
+    if (m->tp > 1 && (getenv("NL_NO_TP_PREFILL") || n < m->tp)) return false;
     for (const Layer &ly : m->L)
         for (const DevMat *w : {&ly.wq, &ly.wk, &ly.wv, &ly.wo, &ly.wgate, &ly.wup, &ly.wdown})
             if (!gemm_eligible(*w)) return false;
@@ -1083,6 +1216,8 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     const nl_config &c = m->c;
     const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, S = c.seq_len, ld = qdim + 2 * kvd;
     cudaStream_t st = m->st;
+    const bool tpar = m->tp > 1;
+    float *pf_part = tpar ? reinterpret_cast<float *>(m->tp_win + m->tp_lay.pf_part) : nullptr;
     { int rc0 = ensure_pf(m); if (rc0) return rc0; }
     NL_CUDA(cudaMemcpyAsync(m->d_prompt, tokens, (size_t)n * 4, cudaMemcpyHostToDevice, st));
     NL_CUDA(cudaStreamSynchronize(st));   // tokens is caller memory
@@ -1107,7 +1242,12 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
         a.scale = (float)(1.0 / sqrt((double)m->hd));
         rope_kv_kernel<<<n, 256, 0, st>>>(a);
         attn_prefill_kernel<<<dim3(m->nH, (n + 31) / 32), 256, 0, st>>>(a);
-        if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st))) return rc;
+        if (tpar) {   // row-split o-projection: this rank's partial, then the reduce-scatter / all-gather of the rows (nl_tp.cuh)
+            if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, pf_part, dim, GEPI_STORE, st))) return rc;
+            tp_reduce_rows_kernel<<<m->opts.num_sms, 256, 0, st>>>(n, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
+            tp_rows_done_kernel<<<1, 32, 0, st>>>(m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
+            m->pf_launches += 2;
+        } else if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st))) return rc;
         rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
         if ((rc = gemm_run(ly.wgate, m->pf_hi, m->pf_lo, n, nullptr, m->pf_g, ffn, GEPI_STORE, st))) return rc;
         if ((rc = gemm_run(ly.wup, m->pf_hi, m->pf_lo, n, nullptr, m->pf_u, ffn, GEPI_STORE, st))) return rc;
@@ -1115,14 +1255,23 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
             const int64_t ne = (int64_t)n * ffn;
             swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
         }
-        if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, m->pf_x, dim, GEPI_RESID, st))) return rc;
+        if (tpar) {
+            if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, pf_part, dim, GEPI_STORE, st))) return rc;
+            tp_reduce_rows_kernel<<<m->opts.num_sms, 256, 0, st>>>(n, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
+            tp_rows_done_kernel<<<1, 32, 0, st>>>(m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
+            m->pf_launches += 2;
+        } else if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, m->pf_x, dim, GEPI_RESID, st))) return rc;
     }
     // the reference computes the LM head at every prompt position and uses only the last (go/main.go:160-166): last row only
     NL_CUDA(cudaMemcpyAsync(m->x, m->pf_x + (size_t)(n - 1) * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, st));
-    const DevMat &out = m->output.present() ? m->output : m->tok_embd;
-    MatRef r = {&out, nullptr, nullptr, m->logits, c.vocab_size};
+    const DevMat &out = tpar ? m->lm_view : (m->output.present() ? m->output : m->tok_embd);
+    MatRef r = {&out, nullptr, nullptr, tpar ? m->logits_local : m->logits, tpar ? m->lvocab : c.vocab_size};
     rc = gemv_dispatch(&r, 1, m->x, dim, 1, EPI_STORE, m->output_norm, c.rms_norm_eps, m->xb, m->opts, st, nullptr);
     if (rc) return rc;
+    if (tpar) {   // vocab-split LM head: every rank drops its shard into every window (m->logits points into this rank's window)
+        tp_allgather_logits_kernel<<<1, 1024, 0, st>>>(m->logits_local, m->lvocab, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_lg_epoch);
+        m->pf_launches++;
+    }
     NL_CUDA(cudaGetLastError());
     return NL_OK;
 }
@@ -1173,6 +1322,7 @@ int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int
     rc = prefill_sequential(m, prompt, n_fed, 0); if (rc) return rc;
     int pos = n_fed;
     NL_CUDA(cudaMemsetAsync(m->d_gen_count, 0, 4, m->st));
+    rc = set_lg_want(m, 0); if (rc) return rc;   // the loop below feeds argmax pairs back on the device: no logits cross NVLink
     // each step: sample (argmax), then Forward(next, pos), pos++, stop when pos >= seq_len (go/main.go:173-218).
     // EOS is only visible on the host, so run in chunks and trim.
     int produced = 0; bool done = false;
@@ -1184,7 +1334,7 @@ int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int
             if (pos >= S) {  // the reference samples one last token, then Forward would overflow: it breaks after Forward at pos==S-1
                 break;
             }
-            NL_CUDA(cudaGraphLaunch(m->g_step[1], m->st));
+            NL_CUDA(cudaGraphLaunch(next_graph(m, true), m->st));
             pos++; run++;
         }
         if (run == 0) break;
@@ -1197,7 +1347,7 @@ int nl_generate_greedy(nl_model *m, const int32_t *prompt, int32_t n_prompt, int
         if (pos >= S) done = true;
     }
     *n_out = produced;
-    return NL_OK;
+    return set_lg_want(m, 1);
 }
 
 int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, float *ms_out) {
@@ -1208,10 +1358,12 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
     NL_CUDA(cudaMemcpyAsync(m->d_token, m->h_stage, 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemcpyAsync(m->d_pos, m->h_stage + 64, 4, cudaMemcpyHostToDevice, m->st));
     NL_CUDA(cudaMemsetAsync(m->d_gen_count, 0, 4, m->st));
+    rc = set_lg_want(m, 0); if (rc) return rc;
     NL_CUDA(cudaEventRecord(m->ev0, m->st));
-    NL_CUDA(cudaGraphLaunch(m->g_fwd[1], m->st));
-    for (int i = 1; i < n_steps; i++) NL_CUDA(cudaGraphLaunch(m->g_step[1], m->st));
+    NL_CUDA(cudaGraphLaunch(next_graph(m, false), m->st));
+    for (int i = 1; i < n_steps; i++) NL_CUDA(cudaGraphLaunch(next_graph(m, true), m->st));
     NL_CUDA(cudaEventRecord(m->ev1, m->st));
+    rc = set_lg_want(m, 1); if (rc) return rc;
     NL_CUDA(cudaStreamSynchronize(m->st));
     NL_CUDA(cudaEventElapsedTime(ms_out, m->ev0, m->ev1));
     if (m->d_trace && getenv("NL_TRACE")) {

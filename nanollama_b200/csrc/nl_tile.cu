@@ -54,8 +54,25 @@ __global__ void tile_q8_0_kernel(const uint4 *__restrict__ qs, const __half *__r
 }
 
 // ---- device helpers ----
+// build-time variants of the streaming loop's inner product (tools/build_variants.py A/Bs them):
+//   NL_TL_ACC     accumulator chains per tile: 2 = one per nibble half (4 dependent MMAs each), 4 / 8 = shorter chains + more adds
+//   NL_TL_MMA_VOL 1 = the MMAs are volatile asm (kept in program order), 0 = the compiler may interleave them with the loads around them
+#ifndef NL_TL_ACC
+#define NL_TL_ACC 2
+#endif
+#ifndef NL_TL_MMA_VOL
+#define NL_TL_MMA_VOL 1
+#endif
+#ifndef NL_TL_DBG_SKIPMATH
+#define NL_TL_DBG_SKIPMATH 0
+#endif
+#if NL_TL_MMA_VOL
+#define TL_MMA_ASM asm volatile
+#else
+#define TL_MMA_ASM asm
+#endif
 __device__ __forceinline__ void mma_f16(float (&c)[4], uint32_t a0, uint32_t a1, uint32_t a2, uint32_t a3, uint32_t b0, uint32_t b1) {
-    asm volatile("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
+    TL_MMA_ASM("mma.sync.aligned.m16n8k16.row.col.f32.f16.f16.f32 {%0,%1,%2,%3}, {%4,%5,%6,%7}, {%8,%9}, {%0,%1,%2,%3};"
                  : "+f"(c[0]), "+f"(c[1]), "+f"(c[2]), "+f"(c[3]) : "r"(a0), "r"(a1), "r"(a2), "r"(a3), "r"(b0), "r"(b1));
 }
 __device__ __forceinline__ uint32_t pack_h2(float lo, float hi) {
@@ -105,9 +122,6 @@ template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
 #define TL_ATTN_CALL __forceinline__
 #else
 #define TL_ATTN_CALL __noinline__
-#endif
-#ifndef NL_TL_XB_SINGLE
-#define NL_TL_XB_SINGLE 1
 #endif
 
 // ---- flagged pairs: the un-normalised partials of a split attention item travel as 8-byte {value, flag} pairs written by ONE store, so a
@@ -162,6 +176,15 @@ __device__ __forceinline__ uint2 ld_vol_v2(const void *p) {
 __device__ __forceinline__ void ld_item(const float *base, int q, unsigned int (&w)[8]) {
     asm volatile("ld.relaxed.gpu.global.v4.u32 {%0,%1,%2,%3}, [%8];\n\tld.relaxed.gpu.global.v4.u32 {%4,%5,%6,%7}, [%8+16];"
                  : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(base + 8 * (size_t)q) : "memory");
+}
+__device__ __forceinline__ void ld_item_sys(const float *base, int q, unsigned int (&w)[8]) {   // (vectors a peer GPU writes over NVLink)
+    asm volatile("ld.relaxed.sys.global.v4.u32 {%0,%1,%2,%3}, [%8];\n\tld.relaxed.sys.global.v4.u32 {%4,%5,%6,%7}, [%8+16];"
+                 : "=r"(w[0]), "=r"(w[1]), "=r"(w[2]), "=r"(w[3]), "=r"(w[4]), "=r"(w[5]), "=r"(w[6]), "=r"(w[7]) : "l"(base + 8 * (size_t)q) : "memory");
+}
+__device__ __forceinline__ void st_poll_sys(float *p, float v) {   // a polled element in a PEER's arena
+    unsigned int b = __float_as_uint(v);
+    if (b == TL_SENT) b = 0x7FFFFFFFu;
+    asm volatile("st.relaxed.sys.global.u32 [%0], %1;" ::"l"(p), "r"(b) : "memory");
 }
 __device__ __forceinline__ bool item_has_sent(const unsigned int (&w)[8]) {
     return max(max(max(w[0], w[1]), max(w[2], w[3])), max(max(w[4], w[5]), max(w[6], w[7]))) == TL_SENT;   // the sentinel is the largest word
@@ -226,54 +249,113 @@ __device__ __forceinline__ void mbar_arrive_u(uint32_t bar) { asm volatile("mbar
 __device__ __forceinline__ void load_xb(uint32_t xf_lane, int B, bool xact, uint32_t (&xb)[16]) {
     if (xact) {
 #pragma unroll
-        for (int i = 0; i < 4; i++) { const uint4 v = lds128(xf_lane + (uint32_t)B * 512u + 16u * i); xb[4 * i] = v.x; xb[4 * i + 1] = v.y; xb[4 * i + 2] = v.z; xb[4 * i + 3] = v.w; }
+        for (int i = 0; i < 4; i++) { const uint4 v = lds128(xf_lane + (uint32_t)B * (uint32_t)TL_XBG + 16u * i); xb[4 * i] = v.x; xb[4 * i + 1] = v.y; xb[4 * i + 2] = v.z; xb[4 * i + 3] = v.w; }
     }
 }
 // One tile: 16 rows x 4 blocks.  acc0 / acc1: this lane's running sums for (row g, block column t) and (row g+8, t).
-// tile_lane = shared address of the tile + 16 * lane.
-__device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, uint32_t corr_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
+// tile_lane = shared address of the tile + 16 * lane.  rec_addr: this block's record {corr_lo, pb_lo, corr_hi, pb_hi}: the low 16
+// elements (low nibbles, accumulators c) and the high 16 (high nibbles, e) carry their own power-of-two operand scale, so that the
+// producer of a 16-row group can publish its half block without knowing the other half (see "producer-side fragments").
+__device__ __forceinline__ void tile_finish(const float (&c)[4], const float (&e)[4], uint32_t dd, uint32_t rec_addr, float &acc0, float &acc1) {
+    float cl, pl, ch, ph;
+    asm volatile("ld.shared.v4.f32 {%0,%1,%2,%3}, [%4];" : "=f"(cl), "=f"(pl), "=f"(ch), "=f"(ph) : "r"(rec_addr));
+    const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
+    // per half: pb * ((hi + lo columns) - zero_point * sum(x) of the half)
+    const float v0 = fmaf(ph, (e[0] + e[1]) + ch, pl * ((c[0] + c[1]) + cl));
+    const float v1 = fmaf(ph, (e[2] + e[3]) + ch, pl * ((c[2] + c[3]) + cl));
+    acc0 = fmaf(df.x, v0, acc0);
+    acc1 = fmaf(df.y, v1, acc1);
+}
+__device__ __forceinline__ void tile_dot(uint32_t tile_lane, uint32_t d_lane, uint32_t rec_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
     const uint4 wa4 = lds128(tile_lane);
     const uint4 wb4 = lds128(tile_lane + 512u);
     const uint32_t dd = lds32(d_lane);
-    float corr_v, pb;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(corr_v), "=f"(pb) : "r"(corr_addr));
     const uint32_t wa[4] = {wa4.x, wa4.y, wa4.z, wa4.w}, wb[4] = {wb4.x, wb4.y, wb4.z, wb4.w};
-    float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
+    constexpr int NCH = NL_TL_ACC / 2;   // chains per nibble half
+    float cc[NCH][4], ee[NCH][4];
+#pragma unroll
+    for (int k = 0; k < NCH; k++) {
+#pragma unroll
+        for (int j = 0; j < 4; j++) { cc[k][j] = 0.f; ee[k][j] = 0.f; }
+    }
 #pragma unroll
     for (int i = 0; i < 4; i++) {
         const uint32_t a8 = wa[i] >> 8, b8 = wb[i] >> 8;
         // elements 4i..4i+3 (low nibbles): n * 2^-24 as fp16 subnormals; B carries 16 * x * S
-        mma_f16(c, wa[i] & 0x000F000Fu, wb[i] & 0x000F000Fu, a8 & 0x000F000Fu, b8 & 0x000F000Fu, xb[4 * i], xb[4 * i + 1]);
+        mma_f16(cc[i % NCH], wa[i] & 0x000F000Fu, wb[i] & 0x000F000Fu, a8 & 0x000F000Fu, b8 & 0x000F000Fu, xb[4 * i], xb[4 * i + 1]);
         // elements 16+4i..16+4i+3 (high nibbles): 16n * 2^-24; B carries x * S
-        mma_f16(e, wa[i] & 0x00F000F0u, wb[i] & 0x00F000F0u, a8 & 0x00F000F0u, b8 & 0x00F000F0u, xb[4 * i + 2], xb[4 * i + 3]);
+        mma_f16(ee[i % NCH], wa[i] & 0x00F000F0u, wb[i] & 0x00F000F0u, a8 & 0x00F000F0u, b8 & 0x00F000F0u, xb[4 * i + 2], xb[4 * i + 3]);
     }
-    const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
-    const float v0 = ((c[0] + e[0]) + (c[1] + e[1])) + corr_v;   // (hi + lo columns) - 8 * sum(x) of the block
-    const float v1 = ((c[2] + e[2]) + (c[3] + e[3])) + corr_v;
-    acc0 = fmaf(df.x * pb, v0, acc0);
-    acc1 = fmaf(df.y * pb, v1, acc1);
+    float c[4], e[4];
+#pragma unroll
+    for (int j = 0; j < 4; j++) {
+        if constexpr (NCH == 1) { c[j] = cc[0][j]; e[j] = ee[0][j]; }
+        else if constexpr (NCH == 2) { c[j] = cc[0][j] + cc[1][j]; e[j] = ee[0][j] + ee[1][j]; }
+        else { c[j] = (cc[0][j] + cc[1][j]) + (cc[2][j] + cc[3][j]); e[j] = (ee[0][j] + ee[1][j]) + (ee[2][j] + ee[3][j]); }
+    }
+    tile_finish(c, e, dd, rec_addr, acc0, acc1);
 }
 
-// Q8_0 tile: eight MMAs, each on word i (elements 4i..4i+3) of the lane's block; B fragment registers 2i, 2i+1.
-__device__ __forceinline__ void tile_dot_q8(uint32_t tile_lane, uint32_t d_lane, uint32_t corr_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
+// Q8_0 tile: eight MMAs, each on word i (elements 4i..4i+3) of the lane's block; B fragment registers 2i, 2i+1.  Words 0-3 (elements
+// 0-15) go through c, words 4-7 (elements 16-31) through e: the same half-block split as Q4_0.
+__device__ __forceinline__ void tile_dot_q8(uint32_t tile_lane, uint32_t d_lane, uint32_t rec_addr, const uint32_t (&xb)[16], float &acc0, float &acc1) {
     const uint4 a_lo = lds128(tile_lane), a_hi = lds128(tile_lane + 512u), b_lo = lds128(tile_lane + 1024u), b_hi = lds128(tile_lane + 1536u);
     const uint32_t dd = lds32(d_lane);
-    float corr_v, pb;
-    asm volatile("ld.shared.v2.f32 {%0,%1}, [%2];" : "=f"(corr_v), "=f"(pb) : "r"(corr_addr));
     const uint32_t wa[8] = {a_lo.x, a_lo.y, a_lo.z, a_lo.w, a_hi.x, a_hi.y, a_hi.z, a_hi.w};
     const uint32_t wb[8] = {b_lo.x, b_lo.y, b_lo.z, b_lo.w, b_hi.x, b_hi.y, b_hi.z, b_hi.w};
     float c[4] = {0.f, 0.f, 0.f, 0.f}, e[4] = {0.f, 0.f, 0.f, 0.f};
 #pragma unroll
     for (int i = 0; i < 8; i++) {
         const uint32_t ua = wa[i] ^ 0x80808080u, ub = wb[i] ^ 0x80808080u;   // int8 -> q + 128 in every byte
-        if (i & 1) mma_f16(e, ua & 0x00FF00FFu, ub & 0x00FF00FFu, (ua >> 8) & 0x00FF00FFu, (ub >> 8) & 0x00FF00FFu, xb[2 * i], xb[2 * i + 1]);
+        if (i >= 4) mma_f16(e, ua & 0x00FF00FFu, ub & 0x00FF00FFu, (ua >> 8) & 0x00FF00FFu, (ub >> 8) & 0x00FF00FFu, xb[2 * i], xb[2 * i + 1]);
         else mma_f16(c, ua & 0x00FF00FFu, ub & 0x00FF00FFu, (ua >> 8) & 0x00FF00FFu, (ub >> 8) & 0x00FF00FFu, xb[2 * i], xb[2 * i + 1]);
     }
-    const float2 df = __half22float2(*reinterpret_cast<const __half2 *>(&dd));
-    const float v0 = ((c[0] + e[0]) + (c[1] + e[1])) + corr_v;   // (hi + lo columns) - 128 * sum(x) of the block
-    const float v1 = ((c[2] + e[2]) + (c[3] + e[3])) + corr_v;
-    acc0 = fmaf(df.x * pb, v0, acc0);
-    acc1 = fmaf(df.y * pb, v1, acc1);
+    tile_finish(c, e, dd, rec_addr, acc0, acc1);
+}
+
+// ---- producer-side fragments: one 16-lane group holds 16 consecutive elements of the NEXT GEMV's input (a half block: element
+// e0 + lane, e0 a multiple of 16) and publishes them in that GEMV's final form (nl_tile.cuh, TL_IMG_BG).  y = the value the GEMV multiplies
+// (x o w for a normed input), x2 = this lane's contribution to the RMSNorm sum of squares.  All 32 lanes call it; `sel` = 0: this
+// half-warp stores the hi column, 1: the lo column (the two half-warps hold the same 16 values), lane16 = lane & 15.
+// Layout facts (the consumer-side conversion input_frags_body writes the same bytes): block b = e0 >> 5 sits at (b >> 2) * TL_IMG_BG +
+// (b & 3) * 128, hi column first (64 B), lo column at +64; Q4_0: element e' (0..15) of half `pos` is halfword (e' >> 1) & 1 of word
+// 4 * (e' >> 2) + 2 * pos + (e' & 1); Q8_0: halfword (e' >> 1) & 1 of word 8 * pos + 2 * (e' >> 2) + (e' & 1).  A word therefore pairs
+// lanes L and L + 2 with (L & 2) == 0.  Records: 16 bytes per half block behind the block group's 512 fragment bytes.
+// sel = 2: this 16-lane group stores both columns (attention epilogue: the two half-warps hold different half blocks).
+template <int TYPE>
+__device__ __forceinline__ void publish_half_block(uint8_t *img, int e0, int lane16, int sel, float y, float x2) {
+    float mx = fabsf(y);
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, o));
+    // Q4_0: max|y| * S in [2^10, 2^11) (the low-nibble operands carry 16 * y * S); Q8_0: [2^14, 2^15)
+    int es = (TYPE == NL_Q8_0 ? 268 : 264) - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
+    es = es < 27 ? 27 : (es > 227 ? 227 : es);
+    const float S = __uint_as_float((uint32_t)es << 23);
+    const int b = e0 >> 5, pos = (e0 >> 4) & 1;
+    float v = y * S, bs = v, ss = x2;
+#pragma unroll
+    for (int o = 1; o < 16; o <<= 1) { bs += __shfl_xor_sync(0xffffffffu, bs, o); ss += __shfl_xor_sync(0xffffffffu, ss, o); }
+    if (TYPE == NL_Q4_0 && pos == 0) v *= 16.f;
+    const __half hh = __float2half_rn(v);
+    const __half hl = __float2half_rn(v - __half2float(hh));
+    const uint32_t mine = (uint32_t)__half_as_ushort(hh) | ((uint32_t)__half_as_ushort(hl) << 16);   // (hi, lo) of my element
+    const uint32_t other = __shfl_xor_sync(0xffffffffu, mine, 2);
+    uint8_t *bg = img + (size_t)(b >> 2) * TL_IMG_BG;
+    if ((lane16 & 2) == 0) {
+        const int i = lane16 >> 2, j = lane16 & 1;
+        const int word = (TYPE == NL_Q8_0) ? 8 * pos + 2 * i + j : 4 * i + 2 * pos + j;
+        uint8_t *wp = bg + (b & 3) * 128 + word * 4;
+        if (sel != 1) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(wp), "r"((mine & 0xFFFFu) | (other << 16)) : "memory");
+        if (sel != 0) asm volatile("st.relaxed.gpu.global.u32 [%0], %1;" ::"l"(wp + 64), "r"((mine >> 16) | (other & 0xFFFF0000u)) : "memory");
+    }
+    if (lane16 == 1 && sel != 1) {   // the half block's record: one 16-byte store
+        unsigned int cw = __float_as_uint(-7.62939453125e-6f * bs);   // -zero_point * 2^-k * sum(y * S): 8 * 2^-20 = 128 * 2^-24 = 2^-17
+        if (cw == 0xFFFFFFFFu) cw = 0x7FFFFFFFu;
+        const unsigned int pw = (uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23;   // 2^k / S
+        unsigned int sw = __float_as_uint(ss);
+        if (sw == 0xFFFFFFFFu) sw = 0x7FFFFFFFu;
+        asm volatile("st.relaxed.gpu.global.v4.u32 [%0], {%1,%2,%3,%4};" ::"l"(bg + 512 + ((b & 3) * 2 + pos) * 16), "r"(cw), "r"(pw), "r"(sw), "r"(0u) : "memory");
+    }
 }
 
 // ---------------------------------------------------------------------------------------------------------------------
@@ -343,11 +425,16 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
     }
 }
 
-// qkv: this layer's q | k | v vector (polled element by element when `poll`), ao: its attention output
-// (few scalar arguments: they travel in registers; the rest is read from shared memory)
-__device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, const float *qkv, float *ao, AttnT &S, int layer, int item, int nse, int hpi, int pos, int p,
+// (few scalar arguments: they travel in registers; the rest -- this layer's q | k | v vector (polled element by element when `poll`), its
+// attention output, the fragment image of the o-projection's input -- is read from the phase descriptor in shared memory)
+template <int TYPE>
+__device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int item, int nse, int hpi, int pos, int p,
                                              bool prefetched, bool poll, unsigned int oflag) {
     const MegaAttn &at = sh.at;
+    const TilePhase &P = sh.ph[p % 3];
+    const float *qkv = P.x;
+    float *ao = P.out;
+    const int layer = P.layer;
     const int tid = threadIdx.x;
     const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
     unsigned long long *trace = (sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
@@ -523,9 +610,11 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, const float *qk
                 }
             }
         }
-        if (I.nse == 1 || I.sp == 0) {
+        if (I.nse == 1 || I.sp == 0) {   // (uniform per item; tid < gthreads is whole warps)
             const float r = o * (1.0f / den);
-            if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r;
+            if (ao) { if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r; }
+            // the o-projection's input in its final form: every 16-lane group holds one half block of the attention output
+            if (P.out_img) publish_half_block<TYPE>(P.out_img, h * HD + (dd & ~15), dd & 15, 2, r, 0.f);
         }
     }
     CK_AT(9);
@@ -538,7 +627,10 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, const float *qk
 // Math-warp side of one GEMV phase: consume this CTA's band slot by slot.  Inlined into gemv_phase (out of line there), so that its registers (the B
 // fragments, the shared-memory addresses) are allocated for the loop alone, not on top of the phase prologue's.
 // My tiles of slot k are band tiles TS * k + TPW * warp (+1 when TPW == 2); their block group advances by TS mod nbg per slot.
-template <int TYPE>
+// EVEN (Q4_0, nbg even -- every shape but the 576 / 640-column matrices of nano / micro): a warp's two tiles always belong to the same
+// row group (bands start on row groups and slots on even tiles), so the loop body is two tiles in a straight line, one fold, one pair
+// of stores; the general body flushes between the tiles when the second one starts the next row group.
+template <int TYPE, bool EVEN>
 __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic, int it, uint32_t ring_u, uint32_t sh_u) {
     // (six arguments: they travel in registers; more of them went through the stack, i.e. through local memory in the hot loop)
     constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW, D_OFF = TileCfg<TYPE>::D_OFF;
@@ -548,39 +640,36 @@ __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic,
     uint32_t red_lane = sh_u + (uint32_t)offsetof(TlShared, red) + (uint32_t)(warp * 2 * 16 + (lane >> 2)) * 4u;   // &red[0][warp][0][lane >> 2]
     const int g = lane >> 2, t = lane & 3;
     const bool xact = (t == (g >> 1));     // lane that holds B column g (block column g>>1, hi|lo = g&1)
-#if NL_TL_XB_SINGLE
-    uint32_t xb0[16];                      // B fragments of the tile at hand (one set: reloaded per tile, 16 registers fewer)
+    uint32_t xb[16];                       // B fragments of the tile at hand (ONE set, reloaded per tile: a second set spilled)
 #pragma unroll
-    for (int i = 0; i < 16; i++) xb0[i] = 0u;
-#define xb1 xb0
-#else
-    uint32_t xb0[16], xb1[16];             // B fragments of my two tiles (reloaded only when the block group changes)
-#pragma unroll
-    for (int i = 0; i < 16; i++) { xb0[i] = 0u; xb1[i] = 0u; }
-#endif
-    const int t0 = TPW * warp, t1 = t0 + 1;   // my tiles of a slot (t1 only when TPW == 2)
+    for (int i = 0; i < 16; i++) xb[i] = 0u;
+    const int t0 = TPW * warp;             // my first tile of a slot (the second one, t0 + 1, only when TPW == 2)
     uint32_t tile_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)lane * 16u;   // + slot * TL_SLOT_BYTES
     uint32_t d_lane0 = ring_u + (uint32_t)t0 * TILE + (uint32_t)D_OFF + (uint32_t)lane * 4u;
-    uint32_t xf_lane = xfrag_u + (uint32_t)g * 64u, corr_lane = corr_u + (uint32_t)t * 8u;
-    asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(corr_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
+    uint32_t xf_lane = xfrag_u + (uint32_t)g * (uint32_t)TL_XCOL, rec_lane = corr_u + (uint32_t)t * 16u;
+    asm volatile("" : "+r"(tile_lane0), "+r"(d_lane0), "+r"(xf_lane), "+r"(rec_lane), "+r"(red_lane));   // keep them in registers: no re-derivation per slot
     int B = t0 - rg_of(t0, nbg, magic) * nbg;
     const int stepB = TS - rg_of(TS, nbg, magic) * nbg;
-    [[maybe_unused]] int cb0 = -1, cb1 = -1;   // block groups whose fragments xb0 / xb1 hold
-#if NL_TL_XB_SINGLE
-#define cb1 cb0
-#endif
+    int cb = -1;                           // block group whose fragments xb holds
     for (int c0 = 0; c0 < band; c0 += TS, it++) {
         const uint32_t slot = (uint32_t)it % TL_SLOTS;
         const int n = min(TS, band - c0);
         mbar_wait_u(full_u + slot * 8u, ((uint32_t)it / TL_SLOTS) & 1u);
+#if NL_TL_DBG_SKIPMATH   // (forensics, with NL_TILE_DBG=1: what the slot hand-over costs without the tile products)
+        if (false) {
+#else
         if (t0 < n) {
+#endif
             const uint32_t so = slot * (uint32_t)TL_SLOT_BYTES, ro = red_lane + slot * (uint32_t)(TL_CW * 2 * 16 * 4);
             float acc0 = 0.f, acc1 = 0.f;
-            if (B != cb0) { load_xb(xf_lane, B, xact, xb0); cb0 = B; }
-            if constexpr (TYPE == NL_Q8_0) tile_dot_q8(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
-            else tile_dot(tile_lane0 + so, d_lane0 + so, corr_lane + (uint32_t)B * 32u, xb0, acc0, acc1);
+            if (B != cb) { load_xb(xf_lane, B, xact, xb); cb = B; }
+            if constexpr (TYPE == NL_Q8_0) tile_dot_q8(tile_lane0 + so, d_lane0 + so, rec_lane + (uint32_t)B * 64u, xb, acc0, acc1);
+            else tile_dot(tile_lane0 + so, d_lane0 + so, rec_lane + (uint32_t)B * 64u, xb, acc0, acc1);
             uint32_t eo = 0;
-            if (TPW == 2 && t1 < n) {
+            if constexpr (TPW == 2 && EVEN) {   // (t0 + 1 < n and B + 1 < nbg always hold here)
+                load_xb(xf_lane, B + 1, xact, xb); cb = B + 1;
+                tile_dot(tile_lane0 + so + TILE, d_lane0 + so + TILE, rec_lane + (uint32_t)(B + 1) * 64u, xb, acc0, acc1);
+            } else if (TPW == 2 && t0 + 1 < n) {
                 int B1 = B + 1;
                 if (B1 == nbg) {   // my second tile starts the next row group: flush the first
                     acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
@@ -588,11 +677,11 @@ __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic,
                     if (t == 0) { sts32f(ro, acc0); sts32f(ro + 32u, acc1); }
                     acc0 = 0.f; acc1 = 0.f; B1 = 0; eo = 64u;
                 }
-                if (B1 != cb1) { load_xb(xf_lane, B1, xact, xb1); cb1 = B1; }
-                tile_dot(tile_lane0 + so + TILE, d_lane0 + so + TILE, corr_lane + (uint32_t)B1 * 32u, xb1, acc0, acc1);
+                if (B1 != cb) { load_xb(xf_lane, B1, xact, xb); cb = B1; }
+                tile_dot(tile_lane0 + so + TILE, d_lane0 + so + TILE, rec_lane + (uint32_t)B1 * 64u, xb, acc0, acc1);
             }
-            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2);
-            acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 1); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 1);
+            acc0 += __shfl_xor_sync(0xffffffffu, acc0, 2); acc1 += __shfl_xor_sync(0xffffffffu, acc1, 2);
             if (t == 0) { sts32f(ro + eo, acc0); sts32f(ro + eo + 32u, acc1); }
         }
         B += stepB;
@@ -601,10 +690,6 @@ __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic,
         if (lane == 0) mbar_arrive_u(empty_u + slot * 8u);
     }
     return it;
-#if NL_TL_XB_SINGLE
-#undef xb1
-#undef cb1
-#endif
 }
 
 // Phase input -> fp16 hi/lo B fragments in shared memory (xfrag) + per-block corrections (corr); returns this thread's part of the sum
@@ -612,13 +697,14 @@ __device__ TL_STREAM_CALL int stream_band(int band, int nbg, unsigned int magic,
 // exchange (xprev + the ranks' partials in rank order).  ckrow: optional clock64 stamps of tid 0 (slot 15: globaltimer of "first item valid").
 template <int TYPE, int mode>
 __device__ __forceinline__ double input_frags_body(const float *px, const float *pnw, int nitem, int nitem_pad, uint8_t *xfrag, float2 *corr, int tid, int poll_ns,
-                                                   const float *xprev, float *xnext, const float *xparts, int tp, int dim, bool xstore, unsigned long long *ckrow) {
+                                                   const float *xprev, float *xnext, const float *xparts, int tp, int dim, bool xstore, unsigned long long *ckrow,
+                                                   bool xparts_prev_poll = false) {
     // One pass, no grid-wide reduction in front of the conversion: every 32-element block gets its own power-of-two scale S_b
     // (max|y| * S_b in [2^10, 2^11), so 16 * y * S_b stays inside fp16 and the lo terms keep 10+ bits), applied back per block in
     // tile_dot; the RMSNorm scale (one scalar per vector) is applied by the finishing warp to the finished sums:
     // W . (inv * (x o w)) = inv * (W . (x o w)).  The float64 sum of squares is therefore off the critical path.
     double ss = 0.0;
-    constexpr bool in_poll = mode == 1, in_exch = mode == 2;
+    constexpr bool in_poll = mode == 1, in_exch = mode == 2, in_exch_poll = mode == 3;
     const bool normed = pnw != nullptr;
     float wv0[8];   // norm weights of my first item (items beyond the first only exist for dim > 4096: fetched where they are used)
 #pragma unroll
@@ -650,6 +736,26 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
                     reinterpret_cast<float4 *>(xnext)[2 * q] = make_float4(y[0], y[1], y[2], y[3]);
                     reinterpret_cast<float4 *>(xnext)[2 * q + 1] = make_float4(y[4], y[5], y[6], y[7]);
                 }
+            } else if (in_exch_poll) {   // the same sum with every term polled: the residual before this exchange, then the ranks' partials
+                unsigned int xc[8];
+                if (xparts_prev_poll) { ld_item(xprev, q, xc); while (item_has_sent(xc)) ld_item(xprev, q, xc); }
+                else {
+                    const uint4 a = __ldcg(reinterpret_cast<const uint4 *>(xprev) + 2 * q), b = __ldcg(reinterpret_cast<const uint4 *>(xprev) + 2 * q + 1);
+                    xc[0] = a.x; xc[1] = a.y; xc[2] = a.z; xc[3] = a.w; xc[4] = b.x; xc[5] = b.y; xc[6] = b.z; xc[7] = b.w;
+                }
+#pragma unroll
+                for (int i = 0; i < 8; i++) y[i] = __uint_as_float(xc[i]);
+                for (int rr = 0; rr < tp; rr++) {
+                    ld_item_sys(xparts + (size_t)rr * dim, q, xc);
+                    while (item_has_sent(xc)) { if (poll_ns) __nanosleep(poll_ns); ld_item_sys(xparts + (size_t)rr * dim, q, xc); }
+#pragma unroll
+                    for (int i = 0; i < 8; i++) y[i] += __uint_as_float(xc[i]);
+                }
+                if (xstore) {   // the new residual, polled by the exchange after this one
+#pragma unroll
+                    for (int i = 0; i < 8; i++) st_poll(xnext, 8 * q + i, y[i]);
+                }
+                if (r == 0 && ckrow) { ckrow[2] = (unsigned long long)clock64(); ckrow[15] = gtime(); }
             } else if (in_poll) {   // look again until none of my 8 elements reads as the sentinel
                 unsigned int xc[8];
                 ld_item(px, q, xc);
@@ -681,15 +787,14 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
         float mx = 0.f;
 #pragma unroll
         for (int i = 0; i < 8; i++) mx = fmaxf(mx, fabsf(y[i]));
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the four lanes of a block sit next to each other
-        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 2));
+        mx = fmaxf(mx, __shfl_xor_sync(0xffffffffu, mx, 1));   // the two lanes of a 16-element half block sit next to each other
         // Q4_0: max|y| * S in [2^10, 2^11) (the low-nibble operands carry 16 * y * S); Q8_0: [2^14, 2^15)
         int es = (TYPE == NL_Q8_0 ? 268 : 264) - (int)((__float_as_uint(mx) >> 23) & 0xFFu);
         es = es < 27 ? 27 : (es > 227 ? 227 : es);
         const float S = __uint_as_float((uint32_t)es << 23);
         const int b = q >> 2, o = (q & 3) * 8;         // block, offset of my 8 elements inside it
         float bs = 0.f;
-        uint8_t *fb = xfrag + (size_t)(b >> 2) * 512 + (size_t)(2 * (b & 3)) * 64;
+        uint8_t *fb = xfrag + (size_t)(b >> 2) * TL_XBG + (size_t)(2 * (b & 3)) * TL_XCOL;
         if constexpr (TYPE == NL_Q8_0) {
             // MMA i takes elements 4i..4i+3: registers 2i = (e0, e2), 2i+1 = (e1, e3); my 8 elements fill registers o/2 .. o/2+3
             float v[8];
@@ -704,7 +809,7 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
             }
             if (store) {
                 *reinterpret_cast<uint4 *>(fb + o * 2) = make_uint4(h[0], h[1], h[2], h[3]);          // hi column of this block
-                *reinterpret_cast<uint4 *>(fb + 64 + o * 2) = make_uint4(l[0], l[1], l[2], l[3]);     // lo column
+                *reinterpret_cast<uint4 *>(fb + TL_XCOL + o * 2) = make_uint4(l[0], l[1], l[2], l[3]);     // lo column
             }
         } else {
             const int pos = o >> 4, ib = ((o & 15) >> 3) * 2;  // low | high nibble half, first of my two word indices
@@ -723,15 +828,57 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
                 const int reg = 4 * (ib + k) + 2 * pos;
                 if (store) {
                     *reinterpret_cast<uint2 *>(fb + reg * 4) = make_uint2(h0, h1);         // hi column of this block
-                    *reinterpret_cast<uint2 *>(fb + 64 + reg * 4) = make_uint2(l0, l1);    // lo column
+                    *reinterpret_cast<uint2 *>(fb + TL_XCOL + reg * 4) = make_uint2(l0, l1);    // lo column
                 }
             }
         }
         bs += __shfl_xor_sync(0xffffffffu, bs, 1);
-        bs += __shfl_xor_sync(0xffffffffu, bs, 2);
-        // per block: -zero_point * 2^-k * sum(y * S_b) (Q4_0: 8 * 2^-20, Q8_0: 128 * 2^-24 -- both 2^-17) and 2^k / S_b, which undoes
+        // per half block: -zero_point * 2^-k * sum(y * S) (Q4_0: 8 * 2^-20, Q8_0: 128 * 2^-24 -- both 2^-17) and 2^k / S, which undoes
         // the operand scaling (k = 20 | 24)
-        if (store && (q & 3) == 0) corr[b] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23));
+        if (store && (q & 1) == 0) corr[2 * b + (o >> 4)] = make_float2(-7.62939453125e-6f * bs, __uint_as_float((uint32_t)((TYPE == NL_Q8_0 ? 278 : 274) - es) << 23));
+    }
+    return ss;
+}
+// Phase input that arrives as a fragment image (producer-side fragments, nl_tile.cuh): copied into shared memory in 16-byte chunks, every
+// chunk looked at until none of its words reads as the sentinel (a block group is 32 fragment chunks + 8 half-block records; up to
+// four chunks per thread in flight).  Blocks beyond the vector (the last block group's padding) become zero fragments with zero
+// scales.  Returns this thread's part of the sum of squares the producers left in the records.
+__device__ __forceinline__ bool chunk_has_sent(const uint4 &v) { return max(max(v.x, v.y), max(v.z, v.w)) == TL_SENT; }
+__device__ __forceinline__ double input_image_body(const uint8_t *img, int nbg, int nb, uint32_t xfrag_u, uint32_t corr_u, int tid, int poll_ns, unsigned long long *ckrow) {
+    double ss = 0.0;
+    const int n_chunks = nbg * 40;
+    constexpr int BATCH = 4;
+    for (int c0 = tid; c0 < n_chunks; c0 += BATCH * TL_CONSUMERS) {
+        uint4 v[BATCH];
+        const uint8_t *src[BATCH];
+        uint32_t dst[BATCH];
+#pragma unroll
+        for (int j = 0; j < BATCH; j++) {
+            const int c = c0 + j * TL_CONSUMERS;
+            v[j] = make_uint4(0u, 0u, 0u, 0u); src[j] = nullptr; dst[j] = 0u;
+            if (c < n_chunks) {
+                const int bg = (int)__umulhi((unsigned)c, 107374183u), k = c - bg * 40;   // c / 40
+                const int block = 4 * bg + (k < 32 ? (k >> 3) : ((k - 32) >> 1));
+                dst[j] = k < 32 ? xfrag_u + (uint32_t)(bg * TL_XBG + (k >> 2) * TL_XCOL + (k & 3) * 16)
+                                : (corr_u + (uint32_t)(bg * 64 + (k - 32) * 8)) | 1u;   // bit 0: a record
+                if (block < nb) { src[j] = img + (size_t)bg * TL_IMG_BG + k * 16; v[j] = ld_vol_v4(src[j]); }
+            }
+        }
+#pragma unroll
+        for (int j = 0; j < BATCH; j++) {
+            if (dst[j] == 0u) continue;
+            if (src[j]) {
+                while (chunk_has_sent(v[j])) {
+                    if (poll_ns) __nanosleep(poll_ns);
+                    v[j] = ld_vol_v4(src[j]);
+                }
+            }
+            if (j == 0 && c0 == tid && ckrow) { ckrow[2] = (unsigned long long)clock64(); ckrow[15] = gtime(); }
+            if (dst[j] & 1u) {
+                asm volatile("st.shared.v2.u32 [%0], {%1,%2};" ::"r"(dst[j] & ~1u), "r"(v[j].x), "r"(v[j].y) : "memory");
+                ss += (double)__uint_as_float(v[j].z);
+            } else asm volatile("st.shared.v4.u32 [%0], {%1,%2,%3,%4};" ::"r"(dst[j]), "r"(v[j].x), "r"(v[j].y), "r"(v[j].z), "r"(v[j].w) : "memory");
+        }
     }
     return ss;
 }
@@ -755,10 +902,12 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
     if (ckrow) ckrow[1] = (unsigned long long)clock64();
 #endif
     double ss;
-    if (in_exch) ss = input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
+    if (P.in_img) ss = input_image_body(P.in_img, nbg, P.cols >> 5, smem_u32(xfrag), smem_u32(corr), tid, sh.poll_ns, ckrow);
+    else if (in_exch && P.parts) ss = input_frags_body<TYPE, 3>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, P.prev, P.next, P.parts, sh.tp, sh.dim, xstore, ckrow, P.prev_poll != 0);
+    else if (in_exch) ss = input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
     else if (P.in_poll) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
     else ss = input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
-    if (trrow && ckrow && P.in_poll) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
+    if (trrow && ckrow && (P.in_poll || P.in_img || (in_exch && P.parts))) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[3] = (unsigned long long)clock64();
     if (tid == TL_CONSUMERS - 32 && sh.trace2) sh.trace2[((size_t)blockIdx.x * sh.n_phases + p) * 16 + 6] = (unsigned long long)clock64();
@@ -772,8 +921,9 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[4] = (unsigned long long)clock64();
 #endif
-    if (xstore) __threadfence();
-    it = stream_band<TYPE>(band, nbg, P.nbg_magic, it, smem_u32(smem), smem_u32(&sh));
+    if (xstore && !P.parts) __threadfence();
+    if (TileCfg<TYPE>::TPW == 2 && (nbg & 1) == 0) it = stream_band<TYPE, true>(band, nbg, P.nbg_magic, it, smem_u32(smem), smem_u32(&sh));
+    else it = stream_band<TYPE, false>(band, nbg, P.nbg_magic, it, smem_u32(smem), smem_u32(&sh));
     if (trrow) trrow[3] = gtime();
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[5] = (unsigned long long)clock64();
@@ -830,8 +980,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
                 if (it >= A.inflight) mbar_wait_parked(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
                 const uint32_t bytes = (uint32_t)min(TS, band - c0) * TILE;
+                if (A.dbg == 1 || A.dbg >= 3) { mbar_arrive(&sh.full_bar[slot]); continue; }
                 mbar_expect_tx(&sh.full_bar[slot], bytes);
-                bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)c0 * TILE, bytes, &sh.full_bar[slot], policy);
+                bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)(A.dbg == 2 ? c0 % (2 * TS) : c0) * TILE, bytes, &sh.full_bar[slot], policy);
             }
         }
         return;
@@ -849,8 +1000,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
             const float *resid_src = ldg_ptr(&P->resid);
+            uint8_t *out_img = ldg_ptr(&P->out_img);          // producer-side fragments of the next GEMV's input (nl_tile.cuh)
+            const float *out_nw = ldg_ptr(&P->out_nw);
             const int out_poll = __ldg(&P->out_poll), resid_poll = __ldg(&P->resid_poll);   // polled vectors (see st_poll)
             const int exch_out = __ldg(&P->exch_out), par = __ldg(&P->par), cross = __ldg(&P->cross);
+            const unsigned long long exch_off = __ldg(&P->exch_off);
+            const bool want_logits = !A.lg_want || __ldg(A.lg_want) != 0;
             const bool to_peers_logits = A.tp > 1 && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
             const int cols_p = __ldg(&P->cols);
@@ -868,11 +1023,16 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                 const int q_first = rg_of(c0, nbg, magic), q_last = rg_of(c1 - 1, nbg, magic);
                 // the residual of a row group that completes in this slot is fetched before we block on the math warps (not for the first
                 // slot of a phase: only a consumed slot proves that this CTA is past the grid barrier that orders the residual's writers)
-                float resid = 0.f;
+                float resid = 0.f, nwv = 1.f;
                 int q_done = -1;
-                if (epi == TEPI_RESID && c0 > 0 && !exch_out) {
+                if ((epi == TEPI_RESID || out_nw) && !exch_out) {
                     for (int q = q_first; q <= q_last; q++) if ((q + 1) * nbg <= c1) { q_done = q; break; }
-                    if (q_done >= 0 && half == 0) { const int r = (rg0 + q_done) * 16 + row; if (r < rows) resid = resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r); }
+                    if (q_done >= 0) {
+                        const int r = (rg0 + q_done) * 16 + row;
+                        if (out_nw && r < rows) nwv = __ldg(out_nw + r);   // static data
+                        if (epi == TEPI_RESID && c0 > 0 && r < rows) resid = resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r);
+                        else if (epi == TEPI_RESID) q_done = -2 - q_done;   // first slot: the residual is fetched after the wait (-2 - q: nwv is valid)
+                    }
                 }
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
                 if (lane == 0 && c1 == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
@@ -882,6 +1042,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     post = rsqrtf((float)s2 * (1.0f / (float)cols_p) + A.eps);
                 }
                 for (int q = q_first; q <= q_last; q++) {
+                    if (A.dbg == 3 && (q + 1) * nbg > c1) continue;   // (forensics)
                     const int a = max(q * nbg, c0) - c0, b = min((q + 1) * nbg, c1) - c0;   // tiles [a, b) of this slot belong to row group q
                     const int wa = a / TPW, wb = (b - 1) / TPW;   // math warp w owns slot tiles [TPW * w, TPW * w + TPW)
                     // warp w dropped this row group's sums into entry 0, unless its first tile still belonged to the previous group
@@ -901,7 +1062,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     float s = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
                     s += __shfl_xor_sync(0xffffffffu, s, 16);
                     racc += s;
-                    if ((q + 1) * nbg <= c1) {   // last tile of the row group is in this slot: publish its 16 rows
+                    if ((q + 1) * nbg <= c1) {   // last tile of the row group is in this slot: publish its 16 rows (both half-warps hold them)
                         const int rg = rg0 + q;
                         float v = racc * post;
                         racc = 0.f;
@@ -909,23 +1070,36 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                             if ((rg & 1) == 0) gate = v;
                             else {
                                 const int r = (rg >> 1) * 16 + row;
-                                if (half == 0 && r < rows) {                                   // SiLU(gate)*up, go/model.go:604-606
-                                    if (out_poll) st_poll(out, r, silu_f(gate) * v); else out[r] = silu_f(gate) * v;
-                                }
+                                const float hv = r < rows ? silu_f(gate) * v : 0.f;                  // SiLU(gate)*up, go/model.go:604-606
+                                if (out && half == 0 && r < rows) { if (out_poll) st_poll(out, r, hv); else out[r] = hv; }
+                                if (out_img) publish_half_block<TYPE>(out_img, (rg >> 1) * 16, row, half, hv, 0.f);
                             }
                         } else {
                             const int r = rg * 16 + row;
-                            if (half == 0 && r < rows) {
-                                if (bias) v += __ldg(bias + r);
-                                if (exch_out) {          // this rank's partial of a row-split product -> slot `rank` on every rank (NVLink stores)
-                                    for (int rr = 0; rr < A.tp; rr++)
-                                        reinterpret_cast<float *>(A.peers.win[rr] + A.ar_off)[((size_t)par * A.tp + A.rank) * A.dim + r] = v;
-                                } else if (to_peers_logits) {   // vocab-split LM head: my rows of the full logits vector on every rank
-                                    for (int rr = 0; rr < A.tp; rr++) reinterpret_cast<float *>(A.peers.win[rr] + A.lg_off)[(size_t)A.rank * A.lvocab + r] = v;
-                                } else {
-                                    if (epi == TEPI_RESID) v += (q == q_done) ? resid : (resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
-                                    if (out_poll) st_poll(out, r, v); else out[r] = v;
+                            const bool ok = r < rows;
+                            if (bias && ok) v += __ldg(bias + r);
+                            if (exch_out) {          // this rank's partial of a row-split product -> slot `rank` on every rank (NVLink stores)
+                                if (half == 0 && ok) {
+                                    if (poll) {      // polled slots of this token parity's arena: the consumers look at the data itself
+                                        for (int rr = 0; rr < A.tp; rr++)
+                                            st_poll_sys(reinterpret_cast<float *>(A.peers.win[rr] + exch_off) + (size_t)A.rank * A.dim + r, v);
+                                    } else {
+                                        for (int rr = 0; rr < A.tp; rr++)
+                                            reinterpret_cast<float *>(A.peers.win[rr] + A.ar_off)[((size_t)par * A.tp + A.rank) * A.dim + r] = v;
+                                    }
                                 }
+                            } else if (to_peers_logits) {   // vocab-split LM head: my rows of the full logits vector on every rank (when somebody reads them)
+                                if (half == 0 && ok && want_logits)
+                                    for (int rr = 0; rr < A.tp; rr++) reinterpret_cast<float *>(A.peers.win[rr] + A.lg_off)[(size_t)A.rank * A.lvocab + r] = v;
+                            } else {
+                                if (epi == TEPI_RESID && ok) v += (q == q_done) ? resid : (resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                if (out && half == 0 && ok) { if (out_poll) st_poll(out, r, v); else out[r] = v; }
+                                if (out_img) {       // the next GEMV reads RMSNorm(out; out_nw): y = v o w here, 1/rms on its finished sums
+                                    const float w = !out_nw ? 1.f : ((q == q_done || q == -2 - q_done) ? nwv : (ok ? __ldg(out_nw + r) : 1.f));
+                                    publish_half_block<TYPE>(out_img, rg * 16, row, half, ok ? v * w : 0.f, ok ? v * v : 0.f);
+                                }
+                            }
+                            if (half == 0 && ok) {
                                 const int gr = A.tp > 1 ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
                                 if (v > best || (v == best && gr < best_i)) { best = v; best_i = gr; }   // first maximum, go/main.go:400-408
                             }
@@ -943,7 +1117,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
                 }
                 if (lane == 0) {
-                    if (A.tp > 1) {
+                    if (A.tp > 1 && poll) {   // polled pairs: the last thing a rank publishes; the logits it stored before them are ordered by the fence
+                        if (want_logits) __threadfence_system();
+                        for (int rr = 0; rr < A.tp; rr++)
+                            asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2 *>(A.peers.win[rr] + A.amax_off) + A.rank * gridDim.x + blockIdx.x),
+                                         "r"(__float_as_uint(best) == TL_SENT ? 0x7FFFFFFFu : __float_as_uint(best)), "r"((unsigned)best_i) : "memory");
+                    } else if (A.tp > 1) {
                         for (int rr = 0; rr < A.tp; rr++)
                             reinterpret_cast<float2 *>(A.peers.win[rr] + A.amax_off)[A.rank * gridDim.x + blockIdx.x] = make_float2(best, __int_as_float(best_i));
                     } else A.amax[blockIdx.x] = make_float2(best, __int_as_float(best_i));
@@ -997,7 +1176,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
             if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled(sh, P.x, P.out, att, P.layer, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
+                attn_item_tiled<TYPE>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
                 pre = false;
             }
             if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
@@ -1020,7 +1199,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         it = gemv_phase<TYPE>(sh, P, smem, band, u0 == 0, it, p);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
-    if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
+    if (A.tp > 1 && poll) {   // (polled) every CTA of every rank has published its argmax pair, after its logits rows
+        const uint2 *pairs = reinterpret_cast<const uint2 *>(A.peers.win[A.rank] + A.amax_off);
+        for (int i = tid; i < A.tp * G; i += TL_CONSUMERS) {
+            uint2 v;
+            do { asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(pairs + i) : "memory"); } while (v.x == TL_SENT || v.y == TL_SENT);
+        }
+    } else if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
 }
 
 template <int TYPE>

@@ -93,10 +93,25 @@ constexpr int TL_SLOT_BYTES = TL_TS * TL_TILE;     // 36,864
 
 constexpr int TL_SLOTS = 4;
 constexpr int TL_MAX_NBG = 96;                     // block groups per row: cols <= 12,288
-constexpr int TL_XFRAG_BYTES = 57344;              // fp16 hi/lo fragments of the phase input (TL_MAX_NBG * 512 = 48 KB); the attention
-                                                   // phase reuses the buffer and needs 56 KB for 96 cached K/V rows
+// Shared-memory image of the phase input: per 32-element block a hi and a lo column of 16 words.  The B-fragment loads of the streaming
+// loop read 8 columns at once (one lane each, 16 bytes): with 64-byte columns four lanes share a bank group (a 4-way conflict on the
+// busiest shared-memory instruction of the loop); 80-byte columns spread the eight lanes over all 32 banks.
+#ifndef NL_TL_XCOL
+#define NL_TL_XCOL 80
+#endif
+constexpr int TL_XCOL = NL_TL_XCOL;                // bytes between the columns of the shared-memory fragment image (64 = dense)
+constexpr int TL_XBG = 8 * TL_XCOL;                // ... between its block groups
+constexpr int TL_XFRAG_BYTES = TL_MAX_NBG * TL_XBG > 57344 ? TL_MAX_NBG * TL_XBG : 57344;   // the attention phase reuses the buffer and
+                                                   // needs 56 KB for 96 cached K/V rows
 constexpr int TL_MAX_ITEMS = 3;                    // 8-float items per math thread in the prologue
-constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_MAX_NBG * 4 * 8;
+constexpr int TL_CORR_BYTES = TL_MAX_NBG * 4 * 16;  // per 32-element block: {correction, 2^k / S} of its low and of its high 16 elements
+constexpr size_t TL_DYN_SMEM = (size_t)TL_SLOTS * TL_SLOT_BYTES + TL_XFRAG_BYTES + TL_CORR_BYTES;
+// Fragment image of a phase input in global memory ("producer-side fragments"): the phase that PRODUCES a vector also publishes it in
+// the consuming GEMV's final form -- per block group (128 elements) the 512 bytes of fp16 hi | lo B fragments exactly as they sit in
+// shared memory, then per 16-element half block one 16-byte record {correction, 2^k / S, sum of squares, 0}.  The consumer's prologue
+// is load -> check for the sentinel -> st.shared instead of a 150-instruction conversion on every one of the 148 SMs.
+constexpr int TL_IMG_BG = 512 + 4 * 2 * 16;        // image bytes per block group
+inline size_t tile_img_bytes(int cols) { return (size_t)((cols / 32 + 3) / 4) * TL_IMG_BG; }
 
 enum { TEPI_STORE = 0, TEPI_RESID = 1, TEPI_SWIGLU = 2 };
 
@@ -117,6 +132,9 @@ struct TilePhase {
     float *out;               // output vector (PH_ATTN: the attention output); stored with st_poll when out_poll
     const float *resid;       // TEPI_RESID: the vector the product is added to (polled when resid_poll)
     int in_poll, out_poll, resid_poll;   // TileArgs::poll: the vector lives in the single-use arena (see "polled activations" in nl_tile.cu)
+    const uint8_t *in_img;    // non-null: the input arrives as a polled fragment image (x / norm_w are then only used for their length)
+    uint8_t *out_img;         // non-null: publish the outputs as the fragment image of the NEXT GEMV's input (PH_ATTN: the o-projection's)
+    const float *out_nw;      // norm weights of that next GEMV (its input is RMSNorm(out; out_nw)), or null
     // ---- tensor parallel (TileArgs::tp > 1) ----
     int exch_out;             // row-split matrix (O / down): the product is this rank's PARTIAL; it is stored into slot `rank` of
                               // parity `par` of every peer's exchange area instead of being added to the residual
@@ -127,6 +145,12 @@ struct TilePhase {
     int wait_cross;           // `cross` of the previous phase (whose barrier this phase waits on)
     const float *prev;
     float *next;
+    // polled exchange (TileArgs::poll with tp > 1): exch_out stores go to window offset exch_off + (rank * dim + row) * 4 of EVERY rank
+    // (this token parity's arena); an in_exch consumer polls prev (when prev_poll), the tp partial vectors at `parts` and leaves the sum
+    // in `next` (polled by the exchange after it)
+    unsigned long long exch_off;
+    const float *parts;
+    int prev_poll;
 };
 
 struct TileArgs {
@@ -139,6 +163,8 @@ struct TileArgs {
     TpPeers peers;
     unsigned long long ar_off, bar_off, lg_off, amax_off;   // exchange area [2][tp][dim] f32 | barrier counters | full logits | [tp][grid] argmax pairs
     float2 *amax;             // optional [grid]: per CTA (maximum, index as int bits) of the last phase's outputs (device-side greedy)
+    const int *lg_want;       // tensor parallel: nonzero = the caller reads the logits, every rank's shard goes to every window (else only
+                              // the argmax pairs cross NVLink: the greedy / bench loops)
     int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier (single GPU only)
     MegaAttn at;
     float eps;
@@ -147,6 +173,10 @@ struct TileArgs {
     int att_chunk;            // attention: positions per split while the splits last (<= 96 = one pass)
     int att_hpi;              // attention: q heads per item; 0 = as few as still give every item its own CTA, >= group = the whole GQA group
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
+    int dbg;                  // forensics (NL_TILE_DBG; results are garbage): 1 = slots are handed over without copying (what the math
+                              // warps and the phase boundaries cost on their own), 2 = every slot is copied from the band's first two
+                              // slots (L2-resident source: the L2-fed rate), 3 = 1 + the finishing warp skips the partial sums of slots
+                              // that do not complete a row group (build with -DNL_TL_DBG_SKIPMATH=1 to drop the tile products too)
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
     unsigned long long *trace2; // optional: [cta][phase][16] clock64 stamps (tools/trace_fine.py)
 };

@@ -28,6 +28,52 @@ def argmax(logits: np.ndarray, n: int) -> int:
     return int(np.argmax(logits[:n]))  # numpy returns the first occurrence of the maximum
 
 
+def sample_top_k(logits: np.ndarray, vocab: int, temp: float, top_k: int, rng) -> int:
+    """sampleTopK, go/main.go:294-343 (one rng draw when temp > 0)."""
+    if temp <= 0:
+        return argmax(logits, vocab)
+    top_k = min(top_k, vocab)
+    order = np.argsort(-logits[:vocab], kind="stable")[:top_k]  # insertion order of the reference == stable descending
+    vals = logits[order]
+    probs = np.exp(((vals - vals[0]) / np.float32(temp)).astype(np.float64)).astype(np.float32)
+    total = np.float32(0)
+    for p in probs:
+        total = np.float32(total + p)
+    r = np.float32(rng.random()) * total
+    cdf = np.float32(0)
+    for i, p in enumerate(probs):
+        cdf = np.float32(cdf + p)
+        if r <= cdf:
+            return int(order[i])
+    return int(order[0])
+
+
+def sample_top_p(logits: np.ndarray, vocab: int, temp: float, top_p: float, rng) -> int:
+    """sampleTopP, go/main.go:346-398."""
+    if temp <= 0:
+        return argmax(logits, vocab)
+    lg = logits[:vocab]
+    mx = lg.max()
+    p = np.exp(((lg - mx) / np.float32(temp)).astype(np.float64)).astype(np.float32)
+    s = np.float32(0)
+    for v in p:  # fp32 sequential sum like the reference
+        s = np.float32(s + v)
+    p = p * (np.float32(1.0) / s)
+    order = np.argsort(-p, kind="stable")
+    cum = np.float32(0)
+    for i, idx in enumerate(order):
+        cum = np.float32(cum + p[idx])
+        if cum >= top_p:
+            r = np.float32(rng.random()) * cum
+            cdf = np.float32(0)
+            for j in range(i + 1):
+                cdf = np.float32(cdf + p[order[j]])
+                if r <= cdf:
+                    return int(order[j])
+            return int(order[0])
+    return int(order[0])
+
+
 class Engine:
     """go/main.go:143-149."""
 
@@ -43,53 +89,12 @@ class Engine:
         self.rng = random.Random(seed)
         self.decode_token = decode_token or (lambda t: "")
 
-    # -- go/main.go:294-343
+    # -- go/main.go:294-343 / :346-398 on State.Logits
     def sample_top_k(self, temp: float, top_k: int) -> int:
-        logits = self.model.state.logits
-        vocab = self.model.config.vocab_size
-        if temp <= 0:
-            return argmax(logits, vocab)
-        top_k = min(top_k, vocab)
-        order = np.argsort(-logits[:vocab], kind="stable")[:top_k]  # insertion order of the reference == stable descending
-        vals = logits[order]
-        probs = np.exp(((vals - vals[0]) / np.float32(temp)).astype(np.float64)).astype(np.float32)
-        total = np.float32(0)
-        for p in probs:
-            total = np.float32(total + p)
-        r = np.float32(self.rng.random()) * total
-        cdf = np.float32(0)
-        for i, p in enumerate(probs):
-            cdf = np.float32(cdf + p)
-            if r <= cdf:
-                return int(order[i])
-        return int(order[0])
+        return sample_top_k(self.model.state.logits, self.model.config.vocab_size, temp, top_k, self.rng)
 
-    # -- go/main.go:346-398
     def sample_top_p(self, temp: float, top_p: float) -> int:
-        logits = self.model.state.logits
-        vocab = self.model.config.vocab_size
-        if temp <= 0:
-            return argmax(logits, vocab)
-        lg = logits[:vocab]
-        mx = lg.max()
-        p = np.exp(((lg - mx) / np.float32(temp)).astype(np.float64)).astype(np.float32)
-        s = np.float32(0)
-        for v in p:  # fp32 sequential sum like the reference
-            s = np.float32(s + v)
-        p = p * (np.float32(1.0) / s)
-        order = np.argsort(-p, kind="stable")
-        cum = np.float32(0)
-        for i, idx in enumerate(order):
-            cum = np.float32(cum + p[idx])
-            if cum >= top_p:
-                r = np.float32(self.rng.random()) * cum
-                cdf = np.float32(0)
-                for j in range(i + 1):
-                    cdf = np.float32(cdf + p[order[j]])
-                    if r <= cdf:
-                        return int(order[j])
-                return int(order[0])
-        return int(order[0])
+        return sample_top_p(self.model.state.logits, self.model.config.vocab_size, temp, top_p, self.rng)
 
     # -- go/main.go:233-291 (GenerateQuiet); Generate (:152-230) is the same loop plus stdout streaming
     def generate_tokens(self, prompt_tokens: Sequence[int], p: GenParams, on_token: Optional[Callable[[int], None]] = None) -> List[int]:

@@ -269,6 +269,10 @@ class GGUFFile:
                 return i
         return None
 
+    def tensors_in_file_order(self):
+        """(name, info) pairs in the order of the file's tensor table (the dict is filled while the table is parsed)."""
+        return list(self.tensors.items())
+
 
 def load_gguf(path: str, verbose: bool = False) -> GGUFFile:
     """go/gguf.go:289-414."""
@@ -388,6 +392,7 @@ class GGUFWriter:
 
     def __init__(self, path: str):
         self.path = path
+        self.version = GGUF_VERSION
         self.kv: List[Tuple[str, int, Any]] = []
         self.tensors: List[Tuple[str, Any, int, Tuple[int, ...]]] = []
 
@@ -439,7 +444,7 @@ class GGUFWriter:
 
     def write(self):
         with open(self.path, "wb") as f:
-            f.write(struct.pack("<IIQQ", GGUF_MAGIC, GGUF_VERSION, len(self.tensors), len(self.kv)))
+            f.write(struct.pack("<IIQQ", GGUF_MAGIC, self.version, len(self.tensors), len(self.kv)))
             for key, vtype, value in self.kv:
                 self._wkv(f, key, vtype, value)
             off = 0

@@ -738,3 +738,37 @@ def test_engine_device_sampling_same_stream_as_host_sampling(top_p, top_k):
     b = Engine(m, eos_id=-1, seed=123, device_sampling=True).generate_tokens(prompt, p)
     assert len(a) == 40 and a == b, (a, b)
     m.close()
+
+
+# ---------------------------------------------------------------- continuous batching behind /chat (go/serve.go:56,106-108)
+def test_continuous_batcher_matches_single_sequence_generation():
+    """Six requests through ContinuousBatcher on a 4-sequence model (joins and leaves at step boundaries, idle rows in between) against
+    the same requests run alone through Engine.generate_tokens (GenerateQuiet): the same tokens for the same seed.  The batch rows run
+    the small-batch GEMV kernels, the lone sequence the persistent kernel: logits differ by fp32 reassociation only, so a sampled token
+    can only differ where the random number falls within ~1e-6 of a cdf step (at most one request may differ)."""
+    from nanollama_b200.batcher import ContinuousBatcher
+    from nanollama_b200.engine import Engine, GenParams
+    gf = T.SyntheticGGUF("mini", G.GGML_Q4_0, seed=5, seq_len=96, vocab=4096, layers=2)
+    mb = M.load_llama_model(gf, max_batch=4)
+    m1 = M.load_llama_model(gf)
+    reqs = [([1, 5, 99, 1000], GenParams(max_tokens=24, temperature=0.8, top_p=0.9, top_k=50), 1),
+            ([1, 7], GenParams(max_tokens=40, temperature=1.0, top_p=1.0, top_k=8), 2),
+            ([1] + list(range(10, 40)), GenParams(max_tokens=16, temperature=0.0, top_p=0.9, top_k=50), 3),
+            ([1, 4000, 17], GenParams(max_tokens=30, temperature=0.7, top_p=0.5, top_k=50), 4),
+            ([1, 3], GenParams(max_tokens=200, temperature=0.9, top_p=0.95, top_k=50), 5),       # runs to the end of the context
+            ([1, 2222], GenParams(max_tokens=12, temperature=0.8, top_p=1.0, top_k=3), 6)]
+    b = ContinuousBatcher(mb, eos_id=-1)
+    tickets = []
+    for i, (pr, p, s) in enumerate(reqs):
+        tickets.append(b.submit(pr, p, seed=s))
+        b.step(); b.step()                      # arrivals spread over time
+    b.run_until_idle()
+    bad = 0
+    for (pr, p, s), t in zip(reqs, tickets):
+        exp = Engine(m1, eos_id=-1, seed=s).generate_tokens(pr, p)
+        got = t.result(0)
+        assert len(got) > 0
+        bad += int(got != exp)
+    assert bad <= 1, bad
+    assert b.rows_run / b.steps_run > 1.5
+    mb.close(); m1.close()

@@ -20,9 +20,12 @@ def main():
     from nanollama_b200 import tiers as T
     from oracle import oracle as O
 
+    from tests.helpers import WithBias
     cases = [("tiny_mha_qknorm_q8_0", G.load_gguf(os.path.join(ROOT, "tests", "golden", "tiny_mha_qknorm_q8_0.gguf")), 40),
              ("goldie-4L-q4_0", T.SyntheticGGUF("goldie", G.GGML_Q4_0, seed=2, seq_len=128, layers=4, vocab=4096), 24)]
     cases.append(("big-2L-q4_0", T.SyntheticGGUF("big", G.GGML_Q4_0, seed=4, seq_len=64, layers=2, vocab=4096), 8))
+    # all four optional bias tensors under tensor parallelism (q/k/v biases are sharded with their rows, the o bias is added by rank 0)
+    cases.append(("goldie-2L-q4_0+bias", WithBias(T.SyntheticGGUF("goldie", G.GGML_Q4_0, seed=6, seq_len=96, layers=2, vocab=4096), seed=2), 16))
     if world <= 4:
         cases.append(("large-2L-q8_0", T.SyntheticGGUF("large", G.GGML_Q8_0, seed=3, seq_len=64, layers=2, vocab=4096), 8))
     ok = True
@@ -45,6 +48,24 @@ def main():
             if o is not None:
                 exp = o.forward(int(t), pos)
                 worst = max(worst, float(np.abs(m.state.logits - exp).max() / np.abs(exp).max()))
+        # one-pass prefill on the tensor cores under tensor parallelism (row-split GEMMs + reduce-scatter / all-gather of the rows):
+        # last-position logits of a 40-token prompt against the oracle, then decode continues from the prefilled cache
+        if gf.meta.seq_len >= 48:
+            long_prompt = np.concatenate([[1], rng.integers(3, gf.meta.vocab_size, size=39)]).astype(np.int32)
+            m.reset()
+            m.prefill(long_prompt)
+            pf = m.state.logits.copy()
+            nxt = int(long_prompt[3])
+            m.forward(nxt, len(long_prompt))
+            if o is not None:
+                o.reset()
+                for pos, t in enumerate(long_prompt):
+                    exp = o.forward(int(t), pos)
+                w1 = float(np.abs(pf - exp).max() / np.abs(exp).max())
+                exp = o.forward(nxt, len(long_prompt))
+                w2 = float(np.abs(m.state.logits - exp).max() / np.abs(exp).max())
+                print(f"[tp] {name} tp={world}: prefill(40) logits max-rel {w1:.2e}, next decode step {w2:.2e}")
+                ok = ok and w1 < 1e-3 and w2 < 1e-3
         got = m.generate_greedy(prompt, n_new)
         # every rank must hold the same stream (full logits are gathered into every window)
         t = torch.tensor(got.astype(np.int64), device="cuda")
