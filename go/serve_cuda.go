@@ -124,6 +124,9 @@ func (b *Batcher) step() bool {
 	return true
 }
 
+// sampleTopKWith / sampleTopPWith are sampleTopK / sampleTopP (main.go:294-343, :346-398) with the random source passed in instead of
+// read from e.rng -- a two-line refactor of the reference functions (each request keeps its own stream), not shown here.
+
 func (b *Batcher) finish(i int) {
 	s := b.slots[i]
 	b.slots[i] = nil

@@ -383,10 +383,12 @@ static int build_tiled(nl_model *m) {
     // one per token parity (nl_tp.cuh, TpArena).  NL_TILE_POLL=0: shared vectors behind release / acquire grid barriers.
     const int POLL = !(getenv("NL_TILE_POLL") && atoi(getenv("NL_TILE_POLL")) == 0) ? 1 : 0;
     // producer-side fragments (nl_tile.cuh): every vector a GEMV reads is published by its producer as that GEMV's fragment image,
-    // behind the fp32 copy where the residual path still needs one.  NL_TILE_IMG=0: fp32 vectors only, converted by every consumer.
-    const int IMG = (POLL && !(getenv("NL_TILE_IMG") && atoi(getenv("NL_TILE_IMG")) == 0)) ? 1 : 0;
+    // behind the fp32 copy where the residual path still needs one.
+    // Measured (profiles/r02_decode_ab.log): the images do not pay on one GPU -- the split moves from 512 consumer threads to the single
+    // finishing warp of the producer, both on the critical path -- so they are opt-in there (NL_TILE_IMG=1).  The polled tensor-parallel
+    // path always uses them for its two local hand-overs (attention -> o, gate/up -> down).
     const bool tpoll = tpar && POLL;
-    if (tpoll && !IMG) return fail(NL_ERR_UNSUPPORTED, "the polled tensor-parallel path needs the fragment images (unset NL_TILE_IMG=0 or set NL_TILE_POLL=0)");
+    const int IMG = POLL && (tpoll || (getenv("NL_TILE_IMG") && atoi(getenv("NL_TILE_IMG")) != 0)) ? 1 : 0;
     // single GPU, per layer (floats): q|k|v, attention output, post-attention residual, SwiGLU output, layer output; then (IMG) the
     // images of the attention output, the post-attention residual, the SwiGLU output and the layer output
     const size_t f_qkv = 0, f_ao = f_qkv + nqkv, f_xres = f_ao + (IMG ? 0 : qdim), f_hb = f_xres + dim, f_xout = f_hb + (IMG ? 0 : ffn);
@@ -1241,7 +1243,8 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
         a.n_heads = m->nH; a.n_kv_heads = m->nKV; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate; a.eps = c.rms_norm_eps;
         a.scale = (float)(1.0 / sqrt((double)m->hd));
         rope_kv_kernel<<<n, 256, 0, st>>>(a);
-        attn_prefill_kernel<<<dim3(m->nH, (n + 31) / 32), 256, 0, st>>>(a);
+        if (getenv("NL_PREFILL_ATTN_CC")) attn_prefill_kernel<<<dim3(m->nH, (n + 31) / 32), 256, 0, st>>>(a);   // (A/B: the CUDA-core kernel)
+        else attn_prefill_tc_kernel<<<dim3(m->nH, (n + PA_QT - 1) / PA_QT), 256, 0, st>>>(a);
         if (tpar) {   // row-split o-projection: this rank's partial, then the reduce-scatter / all-gather of the rows (nl_tp.cuh)
             if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, pf_part, dim, GEPI_STORE, st))) return rc;
             tp_reduce_rows_kernel<<<m->opts.num_sms, 256, 0, st>>>(n, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);

@@ -882,6 +882,18 @@ __device__ __forceinline__ double input_image_body(const uint8_t *img, int nbg, 
     }
     return ss;
 }
+// The less travelled kinds of phase input: a fragment image (NL_TILE_IMG=1), the tensor-parallel exchanges (polled / behind barriers), a
+// plain vector (layer 0's embedding, the one-phase GEMV of nl_matrix).
+template <int TYPE>
+__device__ __noinline__ double other_input(TlShared &sh, const TilePhase &P, uint8_t *xfrag, bool xstore, unsigned long long *ckrow) {
+    const int tid = threadIdx.x, nbg = P.nbg, nitem = P.cols >> 3, nitem_pad = nbg * 16;
+    float2 *corr = reinterpret_cast<float2 *>(xfrag + TL_XFRAG_BYTES);
+    if (P.in_img) return input_image_body(P.in_img, nbg, P.cols >> 5, smem_u32(xfrag), smem_u32(corr), tid, sh.poll_ns, ckrow);
+    if (P.in_exch && P.parts) return input_frags_body<TYPE, 3>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, P.prev, P.next, P.parts, sh.tp, sh.dim, xstore, ckrow, P.prev_poll != 0);
+    if (P.in_exch) return input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
+    if (P.in_poll) return input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    return input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+}
 // One GEMV phase on the math warps, after the wait for its input: input vector -> fragments, then the streaming loop.  ONE out-of-line
 // function per phase kind (this one and attn_item_tiled) with the conversion and the loop inlined into it: its registers are allocated
 // for the phase alone, and the phase loop of the kernel keeps almost nothing alive across the call.  Anything spilled around here goes to
@@ -901,12 +913,11 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[1] = (unsigned long long)clock64();
 #endif
+    // the single-GPU hot path (a polled fp32 vector) is inlined; every other kind of input goes through one out-of-line function, so that
+    // its code does not weigh on this function's register allocation (the same source has allocated differently across unrelated edits)
     double ss;
-    if (P.in_img) ss = input_image_body(P.in_img, nbg, P.cols >> 5, smem_u32(xfrag), smem_u32(corr), tid, sh.poll_ns, ckrow);
-    else if (in_exch && P.parts) ss = input_frags_body<TYPE, 3>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, P.prev, P.next, P.parts, sh.tp, sh.dim, xstore, ckrow, P.prev_poll != 0);
-    else if (in_exch) ss = input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
-    else if (P.in_poll) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
-    else ss = input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    if (P.in_poll && !P.in_img && !in_exch) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    else ss = other_input<TYPE>(sh, P, xfrag, xstore, ckrow);
     if (trrow && ckrow && (P.in_poll || P.in_img || (in_exch && P.parts))) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[3] = (unsigned long long)clock64();
