@@ -532,7 +532,8 @@ static int build_tiled(nl_model *m) {
     memset(&a, 0, sizeof a);
     a.phases = m->d_tphases; a.n_phases = (int)n_ph; a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = POLL;
     a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.att_hpi = tile_env_int("NL_ATT_HPI", 0, 0, 64); a.amax = m->amax; m->amax_valid = true;
-    a.dbg = tile_env_int("NL_TILE_DBG", 0, 0, 3);
+    a.dbg = tile_env_int("NL_TILE_DBG", 0, 0, 4);
+    a.l2pf = tile_env_int("NL_TILE_L2PF", 4, 0, 64);   // (measured on big: 4 slots ahead +1 %, 12 and more lose: the prefetches compete with the copies)
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_sh); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
     a.at.pos = m->d_pos; a.at.part_acc = m->part_acc; a.at.part_ml = m->part_ml;
@@ -553,6 +554,7 @@ static int build_tiled(nl_model *m) {
         NL_CUDA(cudaMemset(m->d_trace2, 0, (size_t)G * n_ph * 16 * sizeof(unsigned long long)));
         a.trace2 = m->d_trace2;
     }
+    m->targs.slim = (POLL && !tpar && !IMG) ? 1 : 0;
     m->tp_poll = tpoll;
     if (tpoll) {   // parity 1: its own descriptor list and argmax-pair area; the host alternates the two (tile_args_for)
         m->targs.amax_off = m->tp_lay.arena[0] + m->tp_arena.amax;
@@ -1517,10 +1519,12 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
 }
 
 int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmup, int32_t iters, float *ms_out) {
-    if (!w || !ms_out || batch < 1 || batch > 64 || n_copies < 1 || iters < 1) return fail(NL_ERR_INVALID, "bad argument");
+    if (!w || !ms_out || batch < 1 || batch > 4096 || n_copies < 1 || iters < 1) return fail(NL_ERR_INVALID, "bad argument");
     NL_CUDA(cudaSetDevice(w->device));
     int rc = matrix_buffers(w, batch); if (rc) return rc;
     const DevMat src = w->copies[0];
+    const int gemm_min = getenv("NL_GEMM_MIN_BATCH") ? atoi(getenv("NL_GEMM_MIN_BATCH")) : 16;
+    if (batch > 64 && !(batch >= gemm_min && gemm_eligible(src))) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 64 == 0", batch);
     while ((int)w->copies.size() < n_copies) {
         DevMat c = src; c.qs = nullptr; c.d = nullptr;
         NL_CUDA(cudaMalloc(&c.qs, src.qs_bytes));
@@ -1532,10 +1536,13 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     cudaEvent_t e0, e1; NL_CUDA(cudaEventCreate(&e0)); NL_CUDA(cudaEventCreate(&e1));
     const int tiled = batch == 1 ? matrix_tiles(w, n_copies) : 1;
     if (tiled < 0) return tiled;
+    const bool gemm = batch >= gemm_min && gemm_eligible(src);   // the T-row GEMM on the tensor cores (the activation planes are split once, outside the timed loop)
+    if (gemm) { rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * src.cols, w->st); if (rc) return rc; }
     int idx = 0;
     for (int i = 0; i < warmup + iters; i++) {
         if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));
-        if (tiled == 0) { rc = matrix_tiled_gemv(w, idx); if (rc) return rc; }
+        if (gemm) { rc = gemm_run(w->copies[idx], w->xh, w->xl, batch, nullptr, w->out, (int)src.rows, GEPI_STORE, w->st); if (rc) return rc; }
+        else if (tiled == 0) { rc = matrix_tiled_gemv(w, idx); if (rc) return rc; }
         else {
             MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
             rc = gemv_dispatch(&r, 1, w->x, (int)src.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;

@@ -172,6 +172,7 @@ static __global__ void embed_kernel(DevMat e, const int32_t *__restrict__ tokens
             v = raw_elem(e.type, e.qs + (idx / be) * bb, (int)(idx % be));
         }
         if (gamma_map) { int g = gamma_map[tok]; if (g >= 0) v += gamma[(int64_t)g * dim + i]; }
+        if (__float_as_uint(v) == 0xFFFFFFFFu) v = __uint_as_float(0x7FFFFFFFu);   // (one NaN pattern is the sentinel of the polled vectors, nl_tile.cu)
         o[i] = v;
     }
 }

@@ -66,6 +66,9 @@ __global__ void tile_q8_0_kernel(const uint4 *__restrict__ qs, const __half *__r
 #ifndef NL_TL_DBG_SKIPMATH
 #define NL_TL_DBG_SKIPMATH 0
 #endif
+#ifndef NL_TL_FIN_SPIN
+#define NL_TL_FIN_SPIN 0
+#endif
 #if NL_TL_MMA_VOL
 #define TL_MMA_ASM asm volatile
 #else
@@ -93,14 +96,14 @@ __device__ __forceinline__ int rg_of(int r, int nbg, unsigned int magic) { retur
 template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
     return reinterpret_cast<T *>(__ldg(reinterpret_cast<const unsigned long long *>(p)));
 }
-#define TL_TRACE(p, k) do { if (A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
+#define TL_TRACE(p, k) do { if ((!SLIM || NL_TL_FINE_TRACE) && A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
 // fine-grained forensics (compile with -DNL_TL_FINE_TRACE=1; off by default: the stamps cost registers in the phase loop): SM cycle
 // counter (clock64) stamps, 16 per (CTA, phase); see tools/trace_fine.py for the slot meanings
 #ifndef NL_TL_FINE_TRACE
 #define NL_TL_FINE_TRACE 0
 #endif
 #if NL_TL_FINE_TRACE
-#define TL_CK(p, k) do { if (A.trace2) A.trace2[((size_t)blockIdx.x * A.n_phases + (p)) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+#define TL_CK(p, k) do { if ((!SLIM || NL_TL_FINE_TRACE) && A.trace2) A.trace2[((size_t)blockIdx.x * A.n_phases + (p)) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
 #define CK_AT(k) do { if (ck) ck[k] = (unsigned long long)clock64(); } while (0)
 #else
 #define TL_CK(p, k) do { } while (0)
@@ -427,7 +430,7 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
 
 // (few scalar arguments: they travel in registers; the rest -- this layer's q | k | v vector (polled element by element when `poll`), its
 // attention output, the fragment image of the o-projection's input -- is read from the phase descriptor in shared memory)
-template <int TYPE>
+template <int TYPE, bool SLIM>
 __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int item, int nse, int hpi, int pos, int p,
                                              bool prefetched, bool poll, unsigned int oflag) {
     const MegaAttn &at = sh.at;
@@ -437,7 +440,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
     const int layer = P.layer;
     const int tid = threadIdx.x;
     const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
-    unsigned long long *trace = (sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+    unsigned long long *trace = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
     [[maybe_unused]] unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
     constexpr int HD = 64, HALF = 32;
     const int group = I.nh, kvd = at.n_kv_heads * HD;   // "group": the q heads of THIS item (I.h0 .. I.h0 + group - 1)
@@ -502,29 +505,31 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
         cp_async_wait_all();
         tl_bar<TL_CONSUMERS>();
         if (pass == 0) CK_AT(4);
-        {   // scores: 8 threads per position, each with 8 of the 64 dims (two conflict-free 16-byte columns), for every head of the group
-            const int sub = tid & 7;
-            for (int tl = tid >> 3; tl < ((cn + 3) & ~3); tl += TL_CONSUMERS / 8) {   // a warp covers 4 consecutive positions: whole warps agree
-                float4 k0 = make_float4(0.f, 0.f, 0.f, 0.f), k1 = k0;
-                if (tl < cn) { k0 = *reinterpret_cast<const float4 *>(&S.Ks[tl][4 * sub]); k1 = *reinterpret_cast<const float4 *>(&S.Ks[tl][32 + 4 * sub]); }
-                float d[MG_MAX_GROUP];   // all heads' partial dots first, then their shuffle chains side by side
+        {   // scores: warp w takes positions w, w + 16, ... (at most six of a pass); lane l holds dims 2l, 2l+1 -- one conflict-free 8-byte
+            // column of every K row.  Per head (a real loop: unrolled over the 8 possible heads the compiler predicates every body, and
+            // a one-head item paid for eight) the six dot products are reduced side by side, five shuffle rounds for all of them.
+            constexpr int NP = (TA_CH + TL_CW - 1) / TL_CW;
+            float2 kk[NP];
 #pragma unroll
-                for (int h2 = 0; h2 < MG_MAX_GROUP; h2++) {
-                    d[h2] = 0.f;
-                    if (h2 < group) {
-                        const float4 q0 = *reinterpret_cast<const float4 *>(&S.q[h2][4 * sub]), q1 = *reinterpret_cast<const float4 *>(&S.q[h2][32 + 4 * sub]);
-                        d[h2] = (fmaf(q0.x, k0.x, q0.y * k0.y) + fmaf(q0.z, k0.z, q0.w * k0.w)) + (fmaf(q1.x, k1.x, q1.y * k1.y) + fmaf(q1.z, k1.z, q1.w * k1.w));
-                    }
+            for (int j = 0; j < NP; j++) {
+                const int tl = warp + TL_CW * j;
+                kk[j] = tl < cn ? *reinterpret_cast<const float2 *>(&S.Ks[tl][2 * lane]) : make_float2(0.f, 0.f);
+            }
+#pragma unroll 1
+            for (int h2 = 0; h2 < group; h2++) {
+                const float2 qq = *reinterpret_cast<const float2 *>(&S.q[h2][2 * lane]);
+                float d[NP];
+#pragma unroll
+                for (int j = 0; j < NP; j++) d[j] = fmaf(qq.x, kk[j].x, qq.y * kk[j].y);
+#pragma unroll
+                for (int o = 16; o > 0; o >>= 1) {
+#pragma unroll
+                    for (int j = 0; j < NP; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
                 }
 #pragma unroll
-                for (int h2 = 0; h2 < MG_MAX_GROUP; h2++) {
-                    if (h2 < group) {   // (uniform)
-                        float v = d[h2];
-                        v += __shfl_xor_sync(0xffffffffu, v, 1);
-                        v += __shfl_xor_sync(0xffffffffu, v, 2);
-                        v += __shfl_xor_sync(0xffffffffu, v, 4);
-                        if (sub == 0 && tl < cn) S.p[h2][tl] = v * at.scale;
-                    }
+                for (int j = 0; j < NP; j++) {
+                    const int tl = warp + TL_CW * j;
+                    if (lane == j && tl < cn) S.p[h2][tl] = d[j] * at.scale;
                 }
             }
         }
@@ -614,7 +619,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
             const float r = o * (1.0f / den);
             if (ao) { if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r; }
             // the o-projection's input in its final form: every 16-lane group holds one half block of the attention output
-            if (P.out_img) publish_half_block<TYPE>(P.out_img, h * HD + (dd & ~15), dd & 15, 2, r, 0.f);
+            if (!SLIM && P.out_img) publish_half_block<TYPE>(P.out_img, h * HD + (dd & ~15), dd & 15, 2, r, 0.f);
         }
     }
     CK_AT(9);
@@ -899,7 +904,7 @@ __device__ __noinline__ double other_input(TlShared &sh, const TilePhase &P, uin
 // for the phase alone, and the phase loop of the kernel keeps almost nothing alive across the call.  Anything spilled around here goes to
 // local memory, i.e. to L2 (12 KB of L1 are left next to the ring): measured 2x on the whole token when the hot loop spilled its B
 // fragments.  Everything the phase needs beyond the six scalar arguments is read from shared memory.
-template <int TYPE>
+template <int TYPE, bool SLIM>
 __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t *smem, int band, bool first_unit, int it, int p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
@@ -908,15 +913,15 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
     const bool normed = P.norm_w != nullptr, in_exch = P.in_exch != 0;
     const int nitem = P.cols >> 3, nitem_pad = nbg * 16;
     const bool xstore = in_exch && first_unit;   // (the CTA that holds the matrix's first unit) stores the new residual
-    unsigned long long *ckrow = (sh.trace2 && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
-    unsigned long long *trrow = (sh.trace && tid == 0) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+    unsigned long long *ckrow = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace2 && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
+    unsigned long long *trrow = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace && tid == 0) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[1] = (unsigned long long)clock64();
 #endif
     // the single-GPU hot path (a polled fp32 vector) is inlined; every other kind of input goes through one out-of-line function, so that
     // its code does not weigh on this function's register allocation (the same source has allocated differently across unrelated edits)
     double ss;
-    if (P.in_poll && !P.in_img && !in_exch) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    if (SLIM || (P.in_poll && !P.in_img && !in_exch)) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
     else ss = other_input<TYPE>(sh, P, xfrag, xstore, ckrow);
     if (trrow && ckrow && (P.in_poll || P.in_img || (in_exch && P.parts))) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
 #if NL_TL_FINE_TRACE
@@ -943,7 +948,10 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
     return it;
 }
 
-template <int TYPE>
+template <int TYPE, bool SLIM>
+// One CTA of 576 threads = 18 warps per SM.  Registers are handed out per warp, to warps in multiples of four: 20 warps' worth has to fit
+// the 64 K registers, i.e. 96 per thread (that is where __launch_bounds__(576, 1) lands; a cap of 112 compiles without the spills of
+// the phase loop but cannot be launched: "too many blocks in cooperative launch").
 __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileArgs A) {
     constexpr int TILE = TileCfg<TYPE>::TILE, TPW = TileCfg<TYPE>::TPW, TS = TPW * TL_CW;
     extern __shared__ __align__(1024) uint8_t smem[];
@@ -957,14 +965,18 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     const int G = gridDim.x;
     const unsigned int epoch = A.epoch ? __ldg(A.epoch) : 0u;
     const unsigned int flag_base = epoch * (unsigned)(A.n_phases + 1);
-    const bool poll = A.poll != 0;
+    // SLIM: the instantiation for the default single-GPU run (polled fp32 vectors, no fragment images, no tracing, no forensics): every
+    // tensor-parallel, barrier, image and trace branch below folds away, which keeps the code the phase boundaries walk through short
+    const bool poll = SLIM || A.poll != 0;
+    const bool tpar = !SLIM && A.tp > 1;
+    const int dbg = SLIM ? 0 : A.dbg;
     if (warp == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.at);
         for (int i = lane; i < (int)(sizeof(MegaAttn) / 4); i += 32) reinterpret_cast<uint32_t *>(&sh.at)[i] = src[i];
     }
     if (tid == 0) {
-        sh.trace = A.trace; sh.trace2 = A.trace2; sh.n_phases = A.n_phases; sh.poll_ns = A.poll_ns; sh.tp = A.tp; sh.dim = A.dim;
-        sh.ar_mine = A.tp > 1 ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) : nullptr;
+        sh.trace = (SLIM && !NL_TL_FINE_TRACE) ? nullptr : A.trace; sh.trace2 = (SLIM && !NL_TL_FINE_TRACE) ? nullptr : A.trace2; sh.n_phases = A.n_phases; sh.poll_ns = A.poll_ns; sh.tp = A.tp; sh.dim = A.dim;
+        sh.ar_mine = tpar ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) : nullptr;
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -975,26 +987,44 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         if (lane != 0) return;
         uint64_t policy;   // weights are read once per token: keep them from evicting activations / KV / norm weights out of L2
         asm volatile("createpolicy.fractional.L2::evict_first.b64 %0, 1.0;" : "=l"(policy));
-        int it = 0;
-        for (int p = 0; p < A.n_phases; p++) {
-            const TilePhase *P = A.phases + p;
-            if (__ldg(&P->kind) != PH_GEMV) continue;
-            const int nbg = __ldg(&P->nbg), urg = __ldg(&P->unit_rg);
-            int u0, u1;
-            band_of(__ldg(&P->units), blockIdx.x, G, A.g_magic, u0, u1);
-            const int band = (u1 - u0) * urg * nbg;
-            const uint8_t *src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TILE;
-            for (int c0 = 0; c0 < band; c0 += TS, it++) {
-                const int slot = it % TL_SLOTS;
-                if (it >= TL_SLOTS) mbar_wait_parked(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
-                // at most `inflight` copies on the wire: bytes requested but not yet landed are queue in front of every other
-                // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
-                if (it >= A.inflight) mbar_wait_parked(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
-                const uint32_t bytes = (uint32_t)min(TS, band - c0) * TILE;
-                if (A.dbg == 1 || A.dbg >= 3) { mbar_arrive(&sh.full_bar[slot]); continue; }
-                mbar_expect_tx(&sh.full_bar[slot], bytes);
-                bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, src + (size_t)(A.dbg == 2 ? c0 % (2 * TS) : c0) * TILE, bytes, &sh.full_bar[slot], policy);
+        // Cursor over this CTA's slots in stream order: (phase, first tile of the slot inside the band).  The copies use one; with
+        // A.l2pf > 0 a second one runs TL_SLOTS + l2pf slots ahead and asks the L2 for those bytes (cp.async.bulk.prefetch.L2): while the
+        // math warps sit at a phase boundary the ring is full and the copies stop, but HBM keeps streaming into the 126 MB L2, and the
+        // slots after the boundary are refilled from there.
+        struct Cur { int p, c0, band; const uint8_t *src; };
+        auto seek = [&](Cur &c) {   // first GEMV phase at or after c.p in which this CTA has tiles (c.p = n_phases: exhausted)
+            for (; c.p < A.n_phases; c.p++) {
+                const TilePhase *P = A.phases + c.p;
+                if (__ldg(&P->kind) != PH_GEMV) continue;
+                const int nbg = __ldg(&P->nbg), urg = __ldg(&P->unit_rg);
+                int u0, u1;
+                band_of(__ldg(&P->units), blockIdx.x, G, A.g_magic, u0, u1);
+                c.band = (u1 - u0) * urg * nbg;
+                if (c.band == 0) continue;
+                c.src = ldg_ptr(&P->tiles) + (size_t)u0 * urg * nbg * TILE;
+                c.c0 = 0;
+                return;
             }
+        };
+        auto advance = [&](Cur &c) { c.c0 += TS; if (c.c0 >= c.band) { c.p++; seek(c); } };
+        Cur cc{0, 0, 0, nullptr}, pc{0, 0, 0, nullptr};
+        seek(cc);
+        int pf_it = 0;
+        if (A.l2pf > 0) { seek(pc); for (; pf_it < TL_SLOTS && pc.p < A.n_phases; pf_it++) advance(pc); }   // the ring itself needs no prefetch
+        for (int it = 0; cc.p < A.n_phases; it++, advance(cc)) {
+            const int slot = it % TL_SLOTS;
+            for (; A.l2pf > 0 && pf_it < it + TL_SLOTS + A.l2pf && pc.p < A.n_phases; pf_it++, advance(pc)) {
+                const uint32_t pbytes = (uint32_t)min(TS, pc.band - pc.c0) * TILE;
+                asm volatile("cp.async.bulk.prefetch.L2.global [%0], %1;" ::"l"(pc.src + (size_t)pc.c0 * TILE), "r"(pbytes) : "memory");
+            }
+            if (it >= TL_SLOTS) mbar_wait_parked(&sh.free_bar[slot], ((it / TL_SLOTS) - 1) & 1);
+            // at most `inflight` copies on the wire: bytes requested but not yet landed are queue in front of every other
+            // request of this SM (barrier polls, the phase input, KV rows), and ~2 slots already cover latency x bandwidth
+            if (it >= A.inflight) mbar_wait_parked(&sh.full_bar[(it - A.inflight) % TL_SLOTS], ((it - A.inflight) / TL_SLOTS) & 1);
+            const uint32_t bytes = (uint32_t)min(TS, cc.band - cc.c0) * TILE;
+            if (dbg == 1 || dbg >= 3) { mbar_arrive(&sh.full_bar[slot]); continue; }   // (forensics: no copy)
+            mbar_expect_tx(&sh.full_bar[slot], bytes);
+            bulk_g2s_hint(ring + (size_t)slot * TL_SLOT_BYTES, cc.src + (size_t)(dbg == 2 ? cc.c0 % (2 * TS) : cc.c0) * TILE, bytes, &sh.full_bar[slot], policy);
         }
         return;
     }
@@ -1011,13 +1041,13 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
             const float *resid_src = ldg_ptr(&P->resid);
-            uint8_t *out_img = ldg_ptr(&P->out_img);          // producer-side fragments of the next GEMV's input (nl_tile.cuh)
-            const float *out_nw = ldg_ptr(&P->out_nw);
+            uint8_t *out_img = SLIM ? nullptr : ldg_ptr(&P->out_img);          // producer-side fragments of the next GEMV's input (nl_tile.cuh)
+            const float *out_nw = SLIM ? nullptr : ldg_ptr(&P->out_nw);
             const int out_poll = __ldg(&P->out_poll), resid_poll = __ldg(&P->resid_poll);   // polled vectors (see st_poll)
-            const int exch_out = __ldg(&P->exch_out), par = __ldg(&P->par), cross = __ldg(&P->cross);
-            const unsigned long long exch_off = __ldg(&P->exch_off);
-            const bool want_logits = !A.lg_want || __ldg(A.lg_want) != 0;
-            const bool to_peers_logits = A.tp > 1 && p == A.n_phases - 1;
+            const int exch_out = SLIM ? 0 : __ldg(&P->exch_out), par = SLIM ? 0 : __ldg(&P->par), cross = SLIM ? 0 : __ldg(&P->cross);
+            const unsigned long long exch_off = SLIM ? 0ull : __ldg(&P->exch_off);
+            const bool want_logits = SLIM || !A.lg_want || __ldg(A.lg_want) != 0;
+            const bool to_peers_logits = tpar && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
             const int cols_p = __ldg(&P->cols);
             int u0, u1;
@@ -1028,6 +1058,83 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             if (lane == 0) TL_CK(p, 8);
             float best = -INFINITY;
             int best_i = 0x7fffffff;
+            // ---- the lean loop: local outputs only (every phase of a single GPU run, the column-split phases of a tensor-parallel one).
+            // One warp walks every slot of the CTA, so each instruction here is latency on the slot recycling path and, for the last slot of a
+            // phase, on the token's critical path: row groups are tracked incrementally (no divides, no searches), whatever the completing
+            // row group needs from memory (bias, residual) is requested before the wait, and the common slot -- 32 tiles of one row group --
+            // is eight fixed loads, one tree, one shuffle.
+            if (!exch_out && !to_peers_logits && !out_img && dbg != 3 && dbg != 4) {
+                int rem = nbg;          // tiles of the current row group still to come
+                int rg = rg0;           // the current row group (of the whole matrix)
+                const float *rb0 = &sh.red[0][0][0][row];
+                for (int c0 = 0; c0 < band; c0 += TS, it++) {
+                    const int slot = it % TL_SLOTS;
+                    const int n = min(TS, band - c0);
+                    const bool done0 = rem <= n;                        // the current row group ends inside this slot
+                    const int r0 = (epi == TEPI_SWIGLU ? (rg >> 1) : rg) * 16 + row;
+                    float bv = 0.f, resid = 0.f;
+                    bool have_resid = false;
+                    if (done0 && r0 < rows && epi != TEPI_SWIGLU) {
+                        if (bias) bv = __ldg(bias + r0);
+                        if (epi == TEPI_RESID && (resid_poll || c0 > 0)) { resid = resid_poll ? ld_poll(resid_src, r0) : __ldcg(resid_src + r0); have_resid = true; }
+                    }
+#if NL_TL_FIN_SPIN
+                    mbar_wait_u(smem_u32(&sh.empty_bar[slot]), (uint32_t)(it / TL_SLOTS) & 1u);
+#else
+                    mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
+#endif
+                    if (lane == 0 && c0 + n == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
+                    if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607 (see the general loop below)
+                        double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);
+                        post = rsqrtf((float)s2 * (1.0f / (float)cols_p) + A.eps);
+                    }
+                    const float *rb = rb0 + slot * (TL_CW * 2 * 16);
+                    int a = 0;                                           // first tile of the slot that belongs to the current row group
+                    bool first = true;
+                    do {
+                        const int take = min(rem, n - a);               // tiles [a, a + take) of this slot belong to row group rg
+                        float pv[TL_CW / 2];
+                        if (take == TS) {                                // the whole slot is one row group: every warp's entry 0
+#pragma unroll
+                            for (int i = 0; i < TL_CW / 2; i++) pv[i] = rb[(half + 2 * i) * 32];
+                        } else {
+                            const int wa = a / TPW, wb = (a + take - 1) / TPW;
+#pragma unroll
+                            for (int i = 0; i < TL_CW / 2; i++) {
+                                const int w = wa + half + 2 * i;         // entry 1 when the warp's first tile still belonged to the group before
+                                pv[i] = (w <= wb) ? rb[w * 32 + ((w == wa && TPW * w < a) ? 16 : 0)] : 0.f;
+                            }
+                        }
+                        float sum = ((pv[0] + pv[1]) + (pv[2] + pv[3])) + ((pv[4] + pv[5]) + (pv[6] + pv[7]));
+                        sum += __shfl_xor_sync(0xffffffffu, sum, 16);
+                        racc += sum;
+                        rem -= take; a += take;
+                        if (rem == 0) {                                  // the row group is complete: publish its 16 rows
+                            float v = racc * post;
+                            racc = 0.f; rem = nbg;
+                            if (epi == TEPI_SWIGLU) {
+                                if ((rg & 1) == 0) gate = v;
+                                else {
+                                    const int r = (rg >> 1) * 16 + row;
+                                    if (half == 0 && r < rows) { const float hv = silu_f(gate) * v; if (out_poll) st_poll(out, r, hv); else out[r] = hv; }   // SiLU(gate)*up, go/model.go:604-606
+                                }
+                            } else {
+                                const int r = rg * 16 + row;
+                                if (half == 0 && r < rows) {
+                                    if (first) v += bv; else if (bias) v += __ldg(bias + r);
+                                    if (epi == TEPI_RESID) v += (first && have_resid) ? resid : (resid_poll ? ld_poll(resid_src, r) : __ldcg(resid_src + r));   // X += W.x, go/model.go:592-594, :610-612
+                                    if (out_poll) st_poll(out, r, v); else out[r] = v;
+                                    if (v > best || (v == best && r < best_i)) { best = v; best_i = r; }   // first maximum, go/main.go:400-408 (LM head)
+                                }
+                            }
+                            rg++;
+                        }
+                        first = false;
+                    } while (a < n);
+                    __syncwarp();
+                    if (lane == 0) mbar_arrive(&sh.free_bar[slot]);
+                }
+            } else
             for (int c0 = 0; c0 < band; c0 += TS, it++) {
                 const int slot = it % TL_SLOTS;
                 const int c1 = min(c0 + TS, band);
@@ -1045,7 +1152,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                         else if (epi == TEPI_RESID) q_done = -2 - q_done;   // first slot: the residual is fetched after the wait (-2 - q: nwv is valid)
                     }
                 }
+#if NL_TL_FIN_SPIN   // (variant: the finishing warp re-issues try_wait instead of parking -- wakes sooner, costs issue slots)
+                mbar_wait_u(smem_u32(&sh.empty_bar[slot]), (uint32_t)(it / TL_SLOTS) & 1u);
+#else
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
+#endif
+                if (dbg == 4) { __syncwarp(); if (lane == 0) mbar_arrive(&sh.free_bar[slot]); continue; }   // (forensics: no finishing work at all)
                 if (lane == 0 && c1 == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
                 if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607: inv = 1 / sqrt(ss / n + eps) from the float64 sum of squares
                     double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);   // fixed butterfly order: deterministic
@@ -1053,7 +1165,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     post = rsqrtf((float)s2 * (1.0f / (float)cols_p) + A.eps);
                 }
                 for (int q = q_first; q <= q_last; q++) {
-                    if (A.dbg == 3 && (q + 1) * nbg > c1) continue;   // (forensics)
+                    if (dbg == 3 && (q + 1) * nbg > c1) continue;   // (forensics)
                     const int a = max(q * nbg, c0) - c0, b = min((q + 1) * nbg, c1) - c0;   // tiles [a, b) of this slot belong to row group q
                     const int wa = a / TPW, wb = (b - 1) / TPW;   // math warp w owns slot tiles [TPW * w, TPW * w + TPW)
                     // warp w dropped this row group's sums into entry 0, unless its first tile still belonged to the previous group
@@ -1111,7 +1223,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                                 }
                             }
                             if (half == 0 && ok) {
-                                const int gr = A.tp > 1 ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
+                                const int gr = tpar ? A.rank * A.lvocab + r : r;   // (only meaningful in the LM-head phase)
                                 if (v > best || (v == best && gr < best_i)) { best = v; best_i = gr; }   // first maximum, go/main.go:400-408
                             }
                         }
@@ -1128,12 +1240,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
                     if (ov > best || (ov == best && oi < best_i)) { best = ov; best_i = oi; }
                 }
                 if (lane == 0) {
-                    if (A.tp > 1 && poll) {   // polled pairs: the last thing a rank publishes; the logits it stored before them are ordered by the fence
+                    if (tpar && poll) {   // polled pairs: the last thing a rank publishes; the logits it stored before them are ordered by the fence
                         if (want_logits) __threadfence_system();
                         for (int rr = 0; rr < A.tp; rr++)
                             asm volatile("st.relaxed.sys.global.v2.u32 [%0], {%1, %2};" ::"l"(reinterpret_cast<float2 *>(A.peers.win[rr] + A.amax_off) + A.rank * gridDim.x + blockIdx.x),
                                          "r"(__float_as_uint(best) == TL_SENT ? 0x7FFFFFFFu : __float_as_uint(best)), "r"((unsigned)best_i) : "memory");
-                    } else if (A.tp > 1) {
+                    } else if (tpar) {
                         for (int rr = 0; rr < A.tp; rr++)
                             reinterpret_cast<float2 *>(A.peers.win[rr] + A.amax_off)[A.rank * gridDim.x + blockIdx.x] = make_float2(best, __int_as_float(best_i));
                     } else A.amax[blockIdx.x] = make_float2(best, __int_as_float(best_i));
@@ -1187,7 +1299,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
             if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled<TYPE>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
+                attn_item_tiled<TYPE, SLIM>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
                 pre = false;
             }
             if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
@@ -1207,23 +1319,23 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
-        it = gemv_phase<TYPE>(sh, P, smem, band, u0 == 0, it, p);
+        it = gemv_phase<TYPE, SLIM>(sh, P, smem, band, u0 == 0, it, p);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
-    if (A.tp > 1 && poll) {   // (polled) every CTA of every rank has published its argmax pair, after its logits rows
+    if (tpar && poll) {   // (polled) every CTA of every rank has published its argmax pair, after its logits rows
         const uint2 *pairs = reinterpret_cast<const uint2 *>(A.peers.win[A.rank] + A.amax_off);
         for (int i = tid; i < A.tp * G; i += TL_CONSUMERS) {
             uint2 v;
             do { asm volatile("ld.relaxed.sys.global.v2.u32 {%0, %1}, [%2];" : "=r"(v.x), "=r"(v.y) : "l"(pairs + i) : "memory"); } while (v.x == TL_SENT || v.y == TL_SENT);
         }
-    } else if (A.tp > 1 && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
+    } else if (tpar && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
 }
 
-template <int TYPE>
+template <int TYPE, bool SLIM>
 static int launch_tiled_t(const TileArgs &a_in, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE, SLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
         configured = true;
     }
     TileArgs a = a_in;
@@ -1234,10 +1346,13 @@ static int launch_tiled_t(const TileArgs &a_in, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they spin on each other
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel<TYPE>, a) == cudaSuccess ? 0 : -2;
+    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel<TYPE, SLIM>, a) == cudaSuccess ? 0 : -2;
 }
+// the lean instantiation when the phase list allows it (TileArgs::slim) and nothing asks for the branches it folds away
 int launch_tiled(int type, const TileArgs &a, int grid, cudaStream_t st) {
-    return type == NL_Q8_0 ? launch_tiled_t<NL_Q8_0>(a, grid, st) : launch_tiled_t<NL_Q4_0>(a, grid, st);
+    const bool slim = a.slim && a.poll && a.tp <= 1 && (NL_TL_FINE_TRACE || (!a.trace && !a.trace2)) && !a.dbg && !getenv("NL_TILE_NO_SLIM");
+    if (type == NL_Q8_0) return slim ? launch_tiled_t<NL_Q8_0, true>(a, grid, st) : launch_tiled_t<NL_Q8_0, false>(a, grid, st);
+    return slim ? launch_tiled_t<NL_Q4_0, true>(a, grid, st) : launch_tiled_t<NL_Q4_0, false>(a, grid, st);
 }
 
 int launch_tile_repack(int type, const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st) {

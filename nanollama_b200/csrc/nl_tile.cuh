@@ -165,7 +165,9 @@ struct TileArgs {
     float2 *amax;             // optional [grid]: per CTA (maximum, index as int bits) of the last phase's outputs (device-side greedy)
     const int *lg_want;       // tensor parallel: nonzero = the caller reads the logits, every rank's shard goes to every window (else only
                               // the argmax pairs cross NVLink: the greedy / bench loops)
-    int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier (single GPU only)
+    int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier
+    int slim;                 // 1: single GPU, polled, every GEMV input is an fp32 vector (no fragment images, no exchanges): launch_tiled may
+                              // take the kernel instantiation without those branches
     MegaAttn at;
     float eps;
     unsigned int g_magic;     // ceil(2^32 / grid), filled in by launch_tiled
@@ -173,10 +175,11 @@ struct TileArgs {
     int att_chunk;            // attention: positions per split while the splits last (<= 96 = one pass)
     int att_hpi;              // attention: q heads per item; 0 = as few as still give every item its own CTA, >= group = the whole GQA group
     int inflight;             // ring copies requested but not yet landed, 1..TL_SLOTS
+    int l2pf;                 // slots beyond the ring that the copy warp keeps requested in L2 (0 = no prefetch)
     int dbg;                  // forensics (NL_TILE_DBG; results are garbage): 1 = slots are handed over without copying (what the math
                               // warps and the phase boundaries cost on their own), 2 = every slot is copied from the band's first two
                               // slots (L2-resident source: the L2-fed rate), 3 = 1 + the finishing warp skips the partial sums of slots
-                              // that do not complete a row group (build with -DNL_TL_DBG_SKIPMATH=1 to drop the tile products too)
+                              // that do not complete a row group, 4 = 1 + no finishing work at all (-DNL_TL_DBG_SKIPMATH=1 drops the tile products too)
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
     unsigned long long *trace2; // optional: [cta][phase][16] clock64 stamps (tools/trace_fine.py)
 };
