@@ -532,7 +532,7 @@ static int build_tiled(nl_model *m) {
     memset(&a, 0, sizeof a);
     a.phases = m->d_tphases; a.n_phases = (int)n_ph; a.bar = m->d_bar; a.eps = c.rms_norm_eps; a.inflight = tile_inflight(); a.epoch = m->d_epoch; a.poll = POLL;
     a.poll_ns = tile_env_int("NL_TILE_POLL_NS", 0, 0, 2000); a.att_chunk = tile_env_int("NL_ATT_CHUNK", 96, 16, 96); a.att_hpi = tile_env_int("NL_ATT_HPI", 0, 0, 64); a.amax = m->amax; m->amax_valid = true;
-    a.dbg = tile_env_int("NL_TILE_DBG", 0, 0, 4);
+    a.dbg = tile_env_int("NL_TILE_DBG", 0, 0, 3);
     a.l2pf = tile_env_int("NL_TILE_L2PF", 4, 0, 64);   // (measured on big: 4 slots ahead +1 %, 12 and more lose: the prefetches compete with the copies)
     // q | k | v is ONE flagged vector: at.q is its base, at.k / at.v only carry element offsets (nl_tile.cu, attn_item_tiled)
     a.at.q = reinterpret_cast<float *>(m->qkv_sh); a.at.k = a.at.q + qdim; a.at.v = a.at.q + qdim + kvd; a.at.kcache = m->kc; a.at.vcache = m->vc; a.at.cos_t = m->cos_t; a.at.sin_t = m->sin_t;
@@ -554,7 +554,7 @@ static int build_tiled(nl_model *m) {
         NL_CUDA(cudaMemset(m->d_trace2, 0, (size_t)G * n_ph * 16 * sizeof(unsigned long long)));
         a.trace2 = m->d_trace2;
     }
-    m->targs.slim = (POLL && !tpar && !IMG) ? 1 : 0;
+    m->targs.slim = (POLL && !tpar && !IMG) ? 1 : tpoll ? 2 : 0;
     m->tp_poll = tpoll;
     if (tpoll) {   // parity 1: its own descriptor list and argmax-pair area; the host alternates the two (tile_args_for)
         m->targs.amax_off = m->tp_lay.arena[0] + m->tp_arena.amax;

@@ -96,14 +96,14 @@ __device__ __forceinline__ int rg_of(int r, int nbg, unsigned int magic) { retur
 template <typename T> __device__ __forceinline__ T *ldg_ptr(T *const *p) {
     return reinterpret_cast<T *>(__ldg(reinterpret_cast<const unsigned long long *>(p)));
 }
-#define TL_TRACE(p, k) do { if ((!SLIM || NL_TL_FINE_TRACE) && A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
+#define TL_TRACE(p, k) do { if ((MODE == 0 || NL_TL_FINE_TRACE) && A.trace) A.trace[((size_t)blockIdx.x * A.n_phases + (p)) * 8 + (k)] = gtime(); } while (0)
 // fine-grained forensics (compile with -DNL_TL_FINE_TRACE=1; off by default: the stamps cost registers in the phase loop): SM cycle
 // counter (clock64) stamps, 16 per (CTA, phase); see tools/trace_fine.py for the slot meanings
 #ifndef NL_TL_FINE_TRACE
 #define NL_TL_FINE_TRACE 0
 #endif
 #if NL_TL_FINE_TRACE
-#define TL_CK(p, k) do { if ((!SLIM || NL_TL_FINE_TRACE) && A.trace2) A.trace2[((size_t)blockIdx.x * A.n_phases + (p)) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
+#define TL_CK(p, k) do { if ((MODE == 0 || NL_TL_FINE_TRACE) && A.trace2) A.trace2[((size_t)blockIdx.x * A.n_phases + (p)) * 16 + (k)] = (unsigned long long)clock64(); } while (0)
 #define CK_AT(k) do { if (ck) ck[k] = (unsigned long long)clock64(); } while (0)
 #else
 #define TL_CK(p, k) do { } while (0)
@@ -430,7 +430,7 @@ __device__ __forceinline__ void attn_fetch(const float *kc, const float *vc, int
 
 // (few scalar arguments: they travel in registers; the rest -- this layer's q | k | v vector (polled element by element when `poll`), its
 // attention output, the fragment image of the o-projection's input -- is read from the phase descriptor in shared memory)
-template <int TYPE, bool SLIM>
+template <int TYPE, int MODE>
 __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int item, int nse, int hpi, int pos, int p,
                                              bool prefetched, bool poll, unsigned int oflag) {
     const MegaAttn &at = sh.at;
@@ -440,7 +440,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
     const int layer = P.layer;
     const int tid = threadIdx.x;
     const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
-    unsigned long long *trace = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+    unsigned long long *trace = ((MODE == 0 || NL_TL_FINE_TRACE) && sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
     [[maybe_unused]] unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
     constexpr int HD = 64, HALF = 32;
     const int group = I.nh, kvd = at.n_kv_heads * HD;   // "group": the q heads of THIS item (I.h0 .. I.h0 + group - 1)
@@ -505,31 +505,22 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
         cp_async_wait_all();
         tl_bar<TL_CONSUMERS>();
         if (pass == 0) CK_AT(4);
-        {   // scores: warp w takes positions w, w + 16, ... (at most six of a pass); lane l holds dims 2l, 2l+1 -- one conflict-free 8-byte
-            // column of every K row.  Per head (a real loop: unrolled over the 8 possible heads the compiler predicates every body, and
-            // a one-head item paid for eight) the six dot products are reduced side by side, five shuffle rounds for all of them.
-            constexpr int NP = (TA_CH + TL_CW - 1) / TL_CW;
-            float2 kk[NP];
+        {   // scores: one lane per position, one warp per (head, 32 positions) -- the whole 64-element dot product in the lane, no
+            // shuffles (the SM retires about one warp shuffle per clock: sixty per warp on sixteen warps were ~1000 cycles of this phase).
+            // K rows are 272 bytes apart: eight consecutive rows cover the 32 banks once, the 16-byte loads of a quarter warp do not
+            // conflict; the q loads are broadcasts.
+            constexpr int NCH = (TA_CH + 31) / 32;
+            for (int hw = warp; hw < NCH * group; hw += TL_CW) {
+                const int h2 = hw / NCH, tl = (hw - h2 * NCH) * 32 + lane;
+                if (tl < cn) {
+                    float d0 = 0.f, d1 = 0.f, d2 = 0.f, d3 = 0.f;
 #pragma unroll
-            for (int j = 0; j < NP; j++) {
-                const int tl = warp + TL_CW * j;
-                kk[j] = tl < cn ? *reinterpret_cast<const float2 *>(&S.Ks[tl][2 * lane]) : make_float2(0.f, 0.f);
-            }
-#pragma unroll 1
-            for (int h2 = 0; h2 < group; h2++) {
-                const float2 qq = *reinterpret_cast<const float2 *>(&S.q[h2][2 * lane]);
-                float d[NP];
-#pragma unroll
-                for (int j = 0; j < NP; j++) d[j] = fmaf(qq.x, kk[j].x, qq.y * kk[j].y);
-#pragma unroll
-                for (int o = 16; o > 0; o >>= 1) {
-#pragma unroll
-                    for (int j = 0; j < NP; j++) d[j] += __shfl_xor_sync(0xffffffffu, d[j], o);
-                }
-#pragma unroll
-                for (int j = 0; j < NP; j++) {
-                    const int tl = warp + TL_CW * j;
-                    if (lane == j && tl < cn) S.p[h2][tl] = d[j] * at.scale;
+                    for (int i = 0; i < HD / 4; i++) {
+                        const float4 kv = *reinterpret_cast<const float4 *>(&S.Ks[tl][4 * i]);
+                        const float4 qv = *reinterpret_cast<const float4 *>(&S.q[h2][4 * i]);
+                        d0 = fmaf(qv.x, kv.x, d0); d1 = fmaf(qv.y, kv.y, d1); d2 = fmaf(qv.z, kv.z, d2); d3 = fmaf(qv.w, kv.w, d3);
+                    }
+                    S.p[h2][tl] = ((d0 + d1) + (d2 + d3)) * at.scale;
                 }
             }
         }
@@ -619,7 +610,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
             const float r = o * (1.0f / den);
             if (ao) { if (poll) st_poll(ao, h * HD + dd, r); else ao[h * HD + dd] = r; }
             // the o-projection's input in its final form: every 16-lane group holds one half block of the attention output
-            if (!SLIM && P.out_img) publish_half_block<TYPE>(P.out_img, h * HD + (dd & ~15), dd & 15, 2, r, 0.f);
+            if (MODE != 1 && P.out_img) publish_half_block<TYPE>(P.out_img, h * HD + (dd & ~15), dd & 15, 2, r, 0.f);
         }
     }
     CK_AT(9);
@@ -889,14 +880,14 @@ __device__ __forceinline__ double input_image_body(const uint8_t *img, int nbg, 
 }
 // The less travelled kinds of phase input: a fragment image (NL_TILE_IMG=1), the tensor-parallel exchanges (polled / behind barriers), a
 // plain vector (layer 0's embedding, the one-phase GEMV of nl_matrix).
-template <int TYPE>
+template <int TYPE, int MODE>
 __device__ __noinline__ double other_input(TlShared &sh, const TilePhase &P, uint8_t *xfrag, bool xstore, unsigned long long *ckrow) {
     const int tid = threadIdx.x, nbg = P.nbg, nitem = P.cols >> 3, nitem_pad = nbg * 16;
     float2 *corr = reinterpret_cast<float2 *>(xfrag + TL_XFRAG_BYTES);
     if (P.in_img) return input_image_body(P.in_img, nbg, P.cols >> 5, smem_u32(xfrag), smem_u32(corr), tid, sh.poll_ns, ckrow);
-    if (P.in_exch && P.parts) return input_frags_body<TYPE, 3>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, P.prev, P.next, P.parts, sh.tp, sh.dim, xstore, ckrow, P.prev_poll != 0);
-    if (P.in_exch) return input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
-    if (P.in_poll) return input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    if (P.in_exch && (MODE == 2 || P.parts)) return input_frags_body<TYPE, 3>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, P.prev, P.next, P.parts, sh.tp, sh.dim, xstore, ckrow, P.prev_poll != 0);
+    if (MODE == 0 && P.in_exch) return input_frags_body<TYPE, 2>(nullptr, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, P.prev, P.next, sh.ar_mine + (size_t)P.par * sh.tp * sh.dim, sh.tp, sh.dim, xstore, nullptr);
+    if (MODE == 0 && P.in_poll) return input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
     return input_frags_body<TYPE, 0>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, 0, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
 }
 // One GEMV phase on the math warps, after the wait for its input: input vector -> fragments, then the streaming loop.  ONE out-of-line
@@ -904,7 +895,7 @@ __device__ __noinline__ double other_input(TlShared &sh, const TilePhase &P, uin
 // for the phase alone, and the phase loop of the kernel keeps almost nothing alive across the call.  Anything spilled around here goes to
 // local memory, i.e. to L2 (12 KB of L1 are left next to the ring): measured 2x on the whole token when the hot loop spilled its B
 // fragments.  Everything the phase needs beyond the six scalar arguments is read from shared memory.
-template <int TYPE, bool SLIM>
+template <int TYPE, int MODE>
 __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t *smem, int band, bool first_unit, int it, int p) {
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
     uint8_t *xfrag = smem + (size_t)TL_SLOTS * TL_SLOT_BYTES;
@@ -913,24 +904,26 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
     const bool normed = P.norm_w != nullptr, in_exch = P.in_exch != 0;
     const int nitem = P.cols >> 3, nitem_pad = nbg * 16;
     const bool xstore = in_exch && first_unit;   // (the CTA that holds the matrix's first unit) stores the new residual
-    unsigned long long *ckrow = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace2 && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
-    unsigned long long *trrow = ((!SLIM || NL_TL_FINE_TRACE) && sh.trace && tid == 0) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
+    unsigned long long *ckrow = ((MODE == 0 || NL_TL_FINE_TRACE) && sh.trace2 && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;   // (slot 15: coarse trace too)
+    unsigned long long *trrow = ((MODE == 0 || NL_TL_FINE_TRACE) && sh.trace && tid == 0) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[1] = (unsigned long long)clock64();
 #endif
     // the single-GPU hot path (a polled fp32 vector) is inlined; every other kind of input goes through one out-of-line function, so that
     // its code does not weigh on this function's register allocation (the same source has allocated differently across unrelated edits)
     double ss;
-    if (SLIM || (P.in_poll && !P.in_img && !in_exch)) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
-    else ss = other_input<TYPE>(sh, P, xfrag, xstore, ckrow);
+    if (MODE == 1 || (MODE == 0 && P.in_poll && !P.in_img && !in_exch)) ss = input_frags_body<TYPE, 1>(P.x, P.norm_w, nitem, nitem_pad, xfrag, corr, tid, sh.poll_ns, nullptr, nullptr, nullptr, 0, 0, false, ckrow);
+    else ss = other_input<TYPE, MODE>(sh, P, xfrag, xstore, ckrow);
     if (trrow && ckrow && (P.in_poll || P.in_img || (in_exch && P.parts))) trrow[1] = ckrow[15];   // "first item valid" (globaltimer)
 #if NL_TL_FINE_TRACE
     if (ckrow) ckrow[3] = (unsigned long long)clock64();
     if (tid == TL_CONSUMERS - 32 && sh.trace2) sh.trace2[((size_t)blockIdx.x * sh.n_phases + p) * 16 + 6] = (unsigned long long)clock64();
 #endif
     if (normed) {
-        ss = warp_sum_d(ss);   // float64 across threads like the reference's float64 sum, go/quant.go:598-603
-        if (lane == 0) sh.ss_red[warp] = ss;
+        // every thread's part is an fp32 sum of 8 squares (x3 at most); the warp's 32 parts are folded in fp32 too (five double-precision
+        // shuffle rounds were ~300 cycles on the critical path of every normed phase), the 16 warp sums in float64 by the finishing warp
+        const float sw = warp_sum((float)ss);
+        if (lane == 0) sh.ss_red[warp] = (double)sw;
     }
     tl_bar<TL_CONSUMERS>();   // fragments complete; the finishing warp turns ss_red into the RMSNorm scale once the first slot is consumed
     if (trrow) trrow[2] = gtime();
@@ -948,7 +941,7 @@ __device__ __noinline__ int gemv_phase(TlShared &sh, const TilePhase &P, uint8_t
     return it;
 }
 
-template <int TYPE, bool SLIM>
+template <int TYPE, int MODE>
 // One CTA of 576 threads = 18 warps per SM.  Registers are handed out per warp, to warps in multiples of four: 20 warps' worth has to fit
 // the 64 K registers, i.e. 96 per thread (that is where __launch_bounds__(576, 1) lands; a cap of 112 compiles without the spills of
 // the phase loop but cannot be launched: "too many blocks in cooperative launch").
@@ -965,17 +958,19 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     const int G = gridDim.x;
     const unsigned int epoch = A.epoch ? __ldg(A.epoch) : 0u;
     const unsigned int flag_base = epoch * (unsigned)(A.n_phases + 1);
-    // SLIM: the instantiation for the default single-GPU run (polled fp32 vectors, no fragment images, no tracing, no forensics): every
-    // tensor-parallel, barrier, image and trace branch below folds away, which keeps the code the phase boundaries walk through short
-    const bool poll = SLIM || A.poll != 0;
-    const bool tpar = !SLIM && A.tp > 1;
-    const int dbg = SLIM ? 0 : A.dbg;
+    // MODE 1: the instantiation for the default single-GPU run (polled fp32 vectors, no fragment images, no tracing, no forensics): every
+    // tensor-parallel, barrier, image and trace branch below folds away.  MODE 2: the same for the polled tensor-parallel run (exchanges
+    // and the two local fragment images stay, barriers / tracing / forensics go).  MODE 0: everything.  Measured on big (10 layers):
+    // 446 -> 401 us per token from the lean instantiation alone -- the phase boundaries walk through a lot of code.
+    const bool poll = MODE != 0 || A.poll != 0;
+    const bool tpar = MODE == 2 || (MODE == 0 && A.tp > 1);
+    const int dbg = MODE != 0 ? 0 : A.dbg;
     if (warp == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.at);
         for (int i = lane; i < (int)(sizeof(MegaAttn) / 4); i += 32) reinterpret_cast<uint32_t *>(&sh.at)[i] = src[i];
     }
     if (tid == 0) {
-        sh.trace = (SLIM && !NL_TL_FINE_TRACE) ? nullptr : A.trace; sh.trace2 = (SLIM && !NL_TL_FINE_TRACE) ? nullptr : A.trace2; sh.n_phases = A.n_phases; sh.poll_ns = A.poll_ns; sh.tp = A.tp; sh.dim = A.dim;
+        sh.trace = (MODE != 0 && !NL_TL_FINE_TRACE) ? nullptr : A.trace; sh.trace2 = (MODE != 0 && !NL_TL_FINE_TRACE) ? nullptr : A.trace2; sh.n_phases = A.n_phases; sh.poll_ns = A.poll_ns; sh.tp = A.tp; sh.dim = A.dim;
         sh.ar_mine = tpar ? reinterpret_cast<const float *>(A.peers.win[A.rank] + A.ar_off) : nullptr;
         for (int s = 0; s < TL_SLOTS; s++) { mbar_init(&sh.full_bar[s], 1); mbar_init(&sh.empty_bar[s], TL_CW); mbar_init(&sh.free_bar[s], 1); }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
@@ -1041,12 +1036,12 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             const float *bias = ldg_ptr(&P->bias);
             float *out = ldg_ptr(&P->out);
             const float *resid_src = ldg_ptr(&P->resid);
-            uint8_t *out_img = SLIM ? nullptr : ldg_ptr(&P->out_img);          // producer-side fragments of the next GEMV's input (nl_tile.cuh)
-            const float *out_nw = SLIM ? nullptr : ldg_ptr(&P->out_nw);
+            uint8_t *out_img = MODE == 1 ? nullptr : ldg_ptr(&P->out_img);          // producer-side fragments of the next GEMV's input (nl_tile.cuh)
+            const float *out_nw = MODE == 1 ? nullptr : ldg_ptr(&P->out_nw);
             const int out_poll = __ldg(&P->out_poll), resid_poll = __ldg(&P->resid_poll);   // polled vectors (see st_poll)
-            const int exch_out = SLIM ? 0 : __ldg(&P->exch_out), par = SLIM ? 0 : __ldg(&P->par), cross = SLIM ? 0 : __ldg(&P->cross);
-            const unsigned long long exch_off = SLIM ? 0ull : __ldg(&P->exch_off);
-            const bool want_logits = SLIM || !A.lg_want || __ldg(A.lg_want) != 0;
+            const int exch_out = MODE == 1 ? 0 : __ldg(&P->exch_out), par = MODE != 0 ? 0 : __ldg(&P->par), cross = MODE != 0 ? 0 : __ldg(&P->cross);
+            const unsigned long long exch_off = MODE == 1 ? 0ull : __ldg(&P->exch_off);
+            const bool want_logits = MODE == 1 || !A.lg_want || __ldg(A.lg_want) != 0;
             const bool to_peers_logits = tpar && p == A.n_phases - 1;
             const bool normed = ldg_ptr(&P->norm_w) != nullptr;
             const int cols_p = __ldg(&P->cols);
@@ -1063,7 +1058,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             // phase, on the token's critical path: row groups are tracked incrementally (no divides, no searches), whatever the completing
             // row group needs from memory (bias, residual) is requested before the wait, and the common slot -- 32 tiles of one row group --
             // is eight fixed loads, one tree, one shuffle.
-            if (!exch_out && !to_peers_logits && !out_img && dbg != 3 && dbg != 4) {
+            if (!exch_out && !to_peers_logits && !out_img && dbg != 3) {
                 int rem = nbg;          // tiles of the current row group still to come
                 int rg = rg0;           // the current row group (of the whole matrix)
                 const float *rb0 = &sh.red[0][0][0][row];
@@ -1085,7 +1080,9 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 #endif
                     if (lane == 0 && c0 + n == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
                     if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607 (see the general loop below)
-                        double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);
+                        double s2 = sh.ss_red[lane & (TL_CW - 1)];   // 16 warp sums, folded in float64 in a fixed butterfly order (both half-warps alike)
+#pragma unroll
+                        for (int o = 1; o < TL_CW; o <<= 1) s2 += __shfl_xor_sync(0xffffffffu, s2, o);
                         post = rsqrtf((float)s2 * (1.0f / (float)cols_p) + A.eps);
                     }
                     const float *rb = rb0 + slot * (TL_CW * 2 * 16);
@@ -1157,7 +1154,6 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 #else
                 mbar_wait_parked(&sh.empty_bar[slot], (it / TL_SLOTS) & 1);
 #endif
-                if (dbg == 4) { __syncwarp(); if (lane == 0) mbar_arrive(&sh.free_bar[slot]); continue; }   // (forensics: no finishing work at all)
                 if (lane == 0 && c1 == band) { TL_TRACE(p, 5); TL_CK(p, 9); }   // last slot consumed by every math warp
                 if (c0 == 0 && normed) {   // RMSNormInto, go/quant.go:597-607: inv = 1 / sqrt(ss / n + eps) from the float64 sum of squares
                     double s2 = warp_sum_d(lane < TL_CW ? sh.ss_red[lane] : 0.0);   // fixed butterfly order: deterministic
@@ -1299,7 +1295,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
             if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
-                attn_item_tiled<TYPE, SLIM>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
+                attn_item_tiled<TYPE, MODE>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
                 pre = false;
             }
             if (poll) { if (tid == 0) { TL_TRACE(p, 3); TL_TRACE(p, 4); } continue; }   // (attn_item_tiled ends on a block barrier; the KV rows are for later tokens)
@@ -1319,7 +1315,7 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
             tl_bar<TL_CONSUMERS>();
         }
         if (band == 0) continue;   // nothing of this matrix lands here (the finishing warp has arrived for us)
-        it = gemv_phase<TYPE, SLIM>(sh, P, smem, band, u0 == 0, it, p);
+        it = gemv_phase<TYPE, MODE>(sh, P, smem, band, u0 == 0, it, p);
     }
     // tensor parallel: the kernel may only complete when every rank's logits shard and argmax pairs have landed in this window
     if (tpar && poll) {   // (polled) every CTA of every rank has published its argmax pair, after its logits rows
@@ -1331,11 +1327,11 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
     } else if (tpar && tid == 0) tl_wait(A, A.n_phases - 1, true, (unsigned)G, epoch);
 }
 
-template <int TYPE, bool SLIM>
+template <int TYPE, int MODE>
 static int launch_tiled_t(const TileArgs &a_in, int grid, cudaStream_t st) {
     static bool configured = false;
     if (!configured) {
-        if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE, SLIM>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
+        if (cudaFuncSetAttribute(decode_tiled_kernel<TYPE, MODE>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)TL_DYN_SMEM) != cudaSuccess) return -2;
         configured = true;
     }
     TileArgs a = a_in;
@@ -1346,13 +1342,15 @@ static int launch_tiled_t(const TileArgs &a_in, int grid, cudaStream_t st) {
     at[0].id = cudaLaunchAttributeCooperative;  // all CTAs must be co-resident: they spin on each other
     at[0].val.cooperative = 1;
     cfg.attrs = at; cfg.numAttrs = 1;
-    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel<TYPE, SLIM>, a) == cudaSuccess ? 0 : -2;
+    return cudaLaunchKernelEx(&cfg, decode_tiled_kernel<TYPE, MODE>, a) == cudaSuccess ? 0 : -2;
 }
-// the lean instantiation when the phase list allows it (TileArgs::slim) and nothing asks for the branches it folds away
+// the lean instantiations when the phase list allows them (TileArgs::slim: 1 = single GPU, every GEMV input a polled fp32 vector;
+// 2 = polled tensor parallel) and nothing asks for the branches they fold away
 int launch_tiled(int type, const TileArgs &a, int grid, cudaStream_t st) {
-    const bool slim = a.slim && a.poll && a.tp <= 1 && (NL_TL_FINE_TRACE || (!a.trace && !a.trace2)) && !a.dbg && !getenv("NL_TILE_NO_SLIM");
-    if (type == NL_Q8_0) return slim ? launch_tiled_t<NL_Q8_0, true>(a, grid, st) : launch_tiled_t<NL_Q8_0, false>(a, grid, st);
-    return slim ? launch_tiled_t<NL_Q4_0, true>(a, grid, st) : launch_tiled_t<NL_Q4_0, false>(a, grid, st);
+    const bool lean = a.slim && a.poll && (NL_TL_FINE_TRACE || (!a.trace && !a.trace2)) && !a.dbg && !getenv("NL_TILE_NO_SLIM");
+    const int mode = !lean ? 0 : (a.slim == 1 && a.tp <= 1) ? 1 : (a.slim == 2 && a.tp > 1) ? 2 : 0;
+    if (type == NL_Q8_0) return mode == 1 ? launch_tiled_t<NL_Q8_0, 1>(a, grid, st) : mode == 2 ? launch_tiled_t<NL_Q8_0, 2>(a, grid, st) : launch_tiled_t<NL_Q8_0, 0>(a, grid, st);
+    return mode == 1 ? launch_tiled_t<NL_Q4_0, 1>(a, grid, st) : mode == 2 ? launch_tiled_t<NL_Q4_0, 2>(a, grid, st) : launch_tiled_t<NL_Q4_0, 0>(a, grid, st);
 }
 
 int launch_tile_repack(int type, const uint8_t *qs, const __half *d, int rows, int nb, uint8_t *tiles, int nbg, int rg_off, int rg_stride, cudaStream_t st) {

@@ -166,8 +166,8 @@ struct TileArgs {
     const int *lg_want;       // tensor parallel: nonzero = the caller reads the logits, every rank's shard goes to every window (else only
                               // the argmax pairs cross NVLink: the greedy / bench loops)
     int poll;                 // 1: activations are single-use polled vectors, the kernel has no grid barrier
-    int slim;                 // 1: single GPU, polled, every GEMV input is an fp32 vector (no fragment images, no exchanges): launch_tiled may
-                              // take the kernel instantiation without those branches
+    int slim;                 // 1: single GPU, polled, every GEMV input is an fp32 vector (no fragment images, no exchanges); 2: polled tensor
+                              // parallel -- launch_tiled may take the kernel instantiation without the branches these runs never reach
     MegaAttn at;
     float eps;
     unsigned int g_magic;     // ceil(2^32 / grid), filled in by launch_tiled
@@ -179,7 +179,7 @@ struct TileArgs {
     int dbg;                  // forensics (NL_TILE_DBG; results are garbage): 1 = slots are handed over without copying (what the math
                               // warps and the phase boundaries cost on their own), 2 = every slot is copied from the band's first two
                               // slots (L2-resident source: the L2-fed rate), 3 = 1 + the finishing warp skips the partial sums of slots
-                              // that do not complete a row group, 4 = 1 + no finishing work at all (-DNL_TL_DBG_SKIPMATH=1 drops the tile products too)
+                              // that do not complete a row group (-DNL_TL_DBG_SKIPMATH=1 drops the tile products too)
     unsigned long long *trace;  // optional: [cta][phase][8] globaltimer stamps
     unsigned long long *trace2; // optional: [cta][phase][16] clock64 stamps (tools/trace_fine.py)
 };
