@@ -686,11 +686,17 @@ static int ensure_pf(nl_model *m) {
     return NL_OK;
 }
 
-// Batched decode on the tensor cores (NL_BATCH_GEMM=1, not validated on a GPU yet -- see DESIGN section 6): B >= 16 sequences are B token
+#ifndef NL_BATCH_GEMM_MIN_DEFAULT
+#define NL_BATCH_GEMM_MIN_DEFAULT 0
+#endif
+// Batched decode on the tensor cores (NL_BATCH_GEMM_MIN): B >= 16 sequences are B token
 // rows of the prefill GEMMs (tcgen05, weights dequantised once per 256 rows) instead of B accumulators of the CUDA-core GEMV, with the
 // per-sequence decode attention in between.  Every kernel on this path already runs in nl_prefill / the batch path.
 static bool batch_gemm_ok(const nl_model *m, int batch) {
-    if (!getenv("NL_BATCH_GEMM") || batch < 16 || m->tp > 1) return false;
+    // NL_BATCH_GEMM_MIN = smallest batch that takes this route (0 = never; the GEMM tiles are 128 rows tall, so a small batch wastes most
+    // of every MMA but still reads the weights once per step instead of once per 4 sequences)
+    const int bmin = getenv("NL_BATCH_GEMM_MIN") ? atoi(getenv("NL_BATCH_GEMM_MIN")) : (getenv("NL_BATCH_GEMM") ? 16 : NL_BATCH_GEMM_MIN_DEFAULT);
+    if (bmin <= 0 || batch < bmin || batch < 2 || m->tp > 1) return false;
     const DevMat &out = m->output.present() ? m->output : m->tok_embd;
     if (!gemm_eligible(out)) return false;
     for (const Layer &ly : m->L)

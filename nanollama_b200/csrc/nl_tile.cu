@@ -387,6 +387,8 @@ __device__ __forceinline__ void cp_async16(void *dst_smem, const void *src) {
 }
 __device__ __forceinline__ void cp_async_wait_all() { asm volatile("cp.async.wait_all;" ::: "memory"); }
 
+// item = (hpi consecutive q heads of one kv head, split of the positions)
+struct AttnItem { int kvh, h0, nh, wr, sp, nse, t_begin, t_end; };
 struct TlShared {
     uint64_t full_bar[TL_SLOTS], empty_bar[TL_SLOTS], free_bar[TL_SLOTS];
     float red[TL_SLOTS][TL_CW][2][16];
@@ -396,11 +398,14 @@ struct TlShared {
     unsigned long long *trace, *trace2;   // (same: TileArgs::trace / trace2, n_phases, poll_ns, tp, dim)
     const float *ar_mine;     // tensor parallel: this rank's exchange area
     int n_phases, poll_ns, tp, dim;
+    // the attention phase's shape is the same in every layer of a token: position, splits, q heads per item, item count and this CTA's
+    // first item are worked out once per launch (a global load and a handful of integer divides per layer otherwise)
+    int a_pos, a_nse, a_hpi, a_items;
+    AttnItem a_item0;
 };
 
 // item = (hpi consecutive q heads of one kv head, split of the positions).  hpi = the whole GQA group shares one pass over the K/V rows;
 // smaller hpi (attn_hpi) spreads a short context over more CTAs -- the rows come from L2 anyway and an item's time is per-head work.
-struct AttnItem { int kvh, h0, nh, wr, sp, nse, t_begin, t_end; };
 __device__ __forceinline__ int attn_hpi(const MegaAttn &at, int nse, int G, int forced) {
     const int group = at.n_heads / at.n_kv_heads;
     if (forced > 0) return forced >= group || group % forced ? group : forced;
@@ -439,7 +444,7 @@ __device__ TL_ATTN_CALL void attn_item_tiled(const TlShared &sh, AttnT &S, int i
     float *ao = P.out;
     const int layer = P.layer;
     const int tid = threadIdx.x;
-    const AttnItem I = attn_locate(at, item, pos + 1, nse, hpi);
+    const AttnItem I = item == (int)blockIdx.x ? sh.a_item0 : attn_locate(at, item, pos + 1, nse, hpi);
     unsigned long long *trace = ((MODE == 0 || NL_TL_FINE_TRACE) && sh.trace && item == (int)blockIdx.x) ? sh.trace + ((size_t)blockIdx.x * sh.n_phases + p) * 8 : nullptr;
     [[maybe_unused]] unsigned long long *ck = (NL_TL_FINE_TRACE && sh.trace2 && item == (int)blockIdx.x && tid == 0) ? sh.trace2 + ((size_t)blockIdx.x * sh.n_phases + p) * 16 : nullptr;
     constexpr int HD = 64, HALF = 32;
@@ -741,11 +746,21 @@ __device__ __forceinline__ double input_frags_body(const float *px, const float 
                 }
 #pragma unroll
                 for (int i = 0; i < 8; i++) y[i] = __uint_as_float(xc[i]);
-                for (int rr = 0; rr < tp; rr++) {
-                    ld_item_sys(xparts + (size_t)rr * dim, q, xc);
-                    while (item_has_sent(xc)) { if (poll_ns) __nanosleep(poll_ns); ld_item_sys(xparts + (size_t)rr * dim, q, xc); }
+                // the ranks' partials, two at a time in flight, added in rank order: one round trip per pair once they have landed
+                // (one rank after the other was tp dependent round trips on the critical path of every exchange)
+                for (int rr = 0; rr < tp; rr += 2) {
+                    const float *pa = xparts + (size_t)rr * dim, *pb = pa + (rr + 1 < tp ? dim : 0);
+                    unsigned int xd[8];
+                    ld_item_sys(pa, q, xc);
+                    ld_item_sys(pb, q, xd);
+                    while (item_has_sent(xc)) { if (poll_ns) __nanosleep(poll_ns); ld_item_sys(pa, q, xc); }
+                    while (item_has_sent(xd)) { if (poll_ns) __nanosleep(poll_ns); ld_item_sys(pb, q, xd); }
 #pragma unroll
                     for (int i = 0; i < 8; i++) y[i] += __uint_as_float(xc[i]);
+                    if (rr + 1 < tp) {
+#pragma unroll
+                        for (int i = 0; i < 8; i++) y[i] += __uint_as_float(xd[i]);
+                    }
                 }
                 if (xstore) {   // the new residual, polled by the exchange after this one
 #pragma unroll
@@ -1256,6 +1271,14 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
 
     // ===================== math warps =====================
     int it = 0;
+    if (tid == 0) {   // the attention phases' shape (the same in every layer)
+        const int pos = A.at.pos ? *A.at.pos : 0, n = pos + 1;   // (a one-phase GEMV launch has no attention state)
+        int nse = (n + max(A.att_chunk, 1) - 1) / max(A.att_chunk, 1);   // one prefetched pass (att_chunk <= 96 positions) per split while the splits last
+        nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
+        const int hpi = A.at.n_kv_heads > 0 ? attn_hpi(A.at, nse, G, A.att_hpi) : 1;
+        sh.a_pos = pos; sh.a_nse = nse; sh.a_hpi = hpi; sh.a_items = A.at.n_kv_heads > 0 ? (A.at.n_heads / hpi) * nse : 0;
+        if (A.at.n_kv_heads > 0) sh.a_item0 = attn_locate(A.at, blockIdx.x, n, nse, hpi);
+    }
     if (warp == 1) {
         const uint32_t *src = reinterpret_cast<const uint32_t *>(&A.phases[0]);
         uint32_t *dst = reinterpret_cast<uint32_t *>(&sh.ph[0]);
@@ -1278,21 +1301,20 @@ __global__ void __launch_bounds__(TL_THREADS, 1) decode_tiled_kernel(const TileA
         const int band = (kind == PH_GEMV) ? (u1 - u0) * P.unit_rg * nbg : 0;
         if (kind == PH_ATTN) {
             tl_bar<TL_CONSUMERS>();   // every math warp is done with the previous phase's fragments: the buffer becomes attention scratch
-            const int pos = *A.at.pos, n = pos + 1;
-            int nse = (n + A.att_chunk - 1) / A.att_chunk;   // one prefetched pass (att_chunk <= 96 positions) per split while the splits last
-            nse = nse < 1 ? 1 : (nse > A.at.nsplit ? A.at.nsplit : nse);
-            const int hpi = attn_hpi(A.at, nse, G, A.att_hpi);
-            const int n_items = (A.at.n_heads / hpi) * nse;
+            const int pos = sh.a_pos, nse = sh.a_nse, hpi = sh.a_hpi, n_items = sh.a_items;
             const int kvd = A.at.n_kv_heads * 64;
             bool pre = false;
             if ((int)blockIdx.x < n_items) {   // cached K/V rows of my first item while q / k / v are still being produced
-                const AttnItem I = attn_locate(A.at, blockIdx.x, n, nse, hpi);
-                attn_fetch(A.at.kcache + (size_t)P.layer * A.at.seq_len * kvd, A.at.vcache + (size_t)P.layer * A.at.seq_len * kvd, kvd, I.kvh, I.t_begin,
-                           min(TA_CH, I.t_end - I.t_begin), pos, att, tid);
+                const int t_begin = sh.a_item0.t_begin;
+                attn_fetch(A.at.kcache + (size_t)P.layer * A.at.seq_len * kvd, A.at.vcache + (size_t)P.layer * A.at.seq_len * kvd, kvd, sh.a_item0.kvh, t_begin,
+                           min(TA_CH, sh.a_item0.t_end - t_begin), pos, att, tid);
                 pre = true;
             }
-            if (tid == 0) { TL_CK(p, 0); TL_TRACE(p, 0); if (!poll) tl_wait(A, p - 1, P.wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
-            tl_bar<TL_CONSUMERS>();
+            if (tid == 0) { TL_CK(p, 0); TL_TRACE(p, 0); }
+            if (!poll) {   // (barrier mode: the wait for q / k / v, handed to the block)
+                if (tid == 0) { tl_wait(A, p - 1, P.wait_cross != 0, (unsigned)G, epoch); TL_TRACE(p, 1); }
+                tl_bar<TL_CONSUMERS>();
+            }
             if (tid == 0) TL_CK(p, 1);
             for (int item = blockIdx.x; item < n_items; item += G) {
                 attn_item_tiled<TYPE, MODE>(sh, att, item, nse, hpi, pos, p, pre, poll, flag_base + (unsigned)p + 1u);
