@@ -17,6 +17,7 @@
 #include <string>
 #include "nl_tp.cuh"
 #include "nl_gemm.cuh"
+#include "nl_gemm2.cuh"
 #include "nl_prefill.cuh"
 
 namespace nl {
@@ -207,13 +208,61 @@ static int gemv_dispatch(const MatRef *mats, int nmat, const float *x, int x_str
 static bool gemm_eligible(const DevMat &w) {
     return (w.type == NL_Q4_0 || w.type == NL_Q8_0 || w.type == NL_F16) && w.cols % GM_BK == 0;
 }
-static int gemm_run(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, const float *bias, float *c, int ldc, int epi, cudaStream_t st) {
+// One launch for up to three matrices that share the input (q|k|v, gate|up): nl_gemm2.cuh.  NL_GEMM_V1=1 keeps the first-generation
+// kernel (one launch per matrix); F16 weights with more than 128 tokens stay with it too (no room for a raw ring next to 16 KB K steps).
+struct GemmOut { const DevMat *w; const float *bias; float *c; int ldc; int epi; };
+static bool gemm_v1() { static const bool v = getenv("NL_GEMM_V1") != nullptr; return v; }
+static int gemm_run1(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, const float *bias, float *c, int ldc, int epi, cudaStream_t st) {
     GemmArgs g; memset(&g, 0, sizeof g);
     g.a_hi = a_hi; g.a_lo = a_lo; g.qs = w.qs; g.d = w.d; g.bias = bias; g.c = c; g.T = T; g.N = (int)w.rows; g.K = (int)w.cols; g.ldc = ldc; g.epi = epi;
     g.swap_lbo_sbo = getenv("NL_GEMM_SWAP") ? 1 : 0;
     int rc = w.type == NL_Q4_0 ? launch_gemm_q4_0(g, st) : w.type == NL_Q8_0 ? launch_gemm_q8_0(g, st) : launch_gemm_f16(g, st);
     if (rc) return fail(NL_ERR_CUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
     return NL_OK;
+}
+constexpr size_t G2_SPLIT_BYTES = 16u << 20;
+static int gemm_run_multi(const GemmOut *o, int n, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, cudaStream_t st, int *launches = nullptr, float *split = nullptr) {
+    bool same = n <= G2_MAX_SEG;
+    for (int i = 1; i < n; i++) same = same && o[i].w->type == o[0].w->type && o[i].w->cols == o[0].w->cols;
+    const bool v1 = gemm_v1() || (o[0].w->type == NL_F16 && T > 128);
+    if (v1 || !same) {
+        for (int i = 0; i < n; i++) {
+            int rc = (v1 || (o[i].w->type == NL_F16 && T > 128)) ? gemm_run1(*o[i].w, a_hi, a_lo, T, o[i].bias, o[i].c, o[i].ldc, o[i].epi, st)
+                                                                 : gemm_run_multi(&o[i], 1, a_hi, a_lo, T, st, nullptr, split);
+            if (rc) return rc;
+            if (launches) (*launches)++;
+        }
+        return NL_OK;
+    }
+    Gemm2Args g; memset(&g, 0, sizeof g);
+    g.a_hi = a_hi; g.a_lo = a_lo; g.nseg = n; g.T = T; g.K = (int)o[0].w->cols;
+    int tiles = 0;
+    for (int i = 0; i < n; i++) {
+        const DevMat &w = *o[i].w;
+        tiles += ((int)w.rows + G2_BN - 1) / G2_BN;
+        g.seg[i].qs = w.qs; g.seg[i].d = w.d; g.seg[i].bias = o[i].bias; g.seg[i].c = o[i].c; g.seg[i].N = (int)w.rows; g.seg[i].ldc = o[i].ldc; g.seg[i].epi = o[i].epi;
+        g.seg[i].tile_end = tiles;
+    }
+    g.ksplit = 1; g.ksplit_steps = g.K / 32; g.ldp = tiles * G2_BN; g.part = split;
+    if (T <= 128 && split && !getenv("NL_GEMM_NOSPLIT")) {
+        // a small batch is bound by how fast the weights stream, and one CTA per 256 rows leaves most SMs idle on the narrow matrices:
+        // enough K splits for one CTA per SM, at least four K steps each, partial sums within the scratch
+        const int nbk = g.K / 32;
+        const int want = 148 / tiles, maxs = nbk / 4 < 16 ? nbk / 4 : 16;   // (one wave: a second one pays the CTA's fixed costs again)
+        const int cap = (int)(G2_SPLIT_BYTES / ((size_t)T * g.ldp * 4));
+        int S = want < maxs ? want : maxs;
+        if (S > cap) S = cap;
+        if (S > 1) { g.ksplit_steps = (nbk + S - 1) / S; g.ksplit = (nbk + g.ksplit_steps - 1) / g.ksplit_steps; }
+    }
+    const int type = o[0].w->type;
+    int rc = type == NL_Q4_0 ? launch_gemm2_q4_0(g, st) : type == NL_Q8_0 ? launch_gemm2_q8_0(g, st) : launch_gemm2_f16(g, st);
+    if (rc) return fail(NL_ERR_CUDA, "tcgen05 GEMM launch failed: %s", cudaGetErrorString(cudaGetLastError()));
+    if (launches) *launches += g.ksplit > 1 ? 2 : 1;
+    return NL_OK;
+}
+static int gemm_run(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, const float *bias, float *c, int ldc, int epi, cudaStream_t st, float *split = nullptr) {
+    const GemmOut o{&w, bias, c, ldc, epi};
+    return gemm_run_multi(&o, 1, a_hi, a_lo, T, st, nullptr, split);
 }
 static int split_planes(const float *x, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t n, cudaStream_t st) {
     const int64_t pairs = (n + 1) / 2;
@@ -264,6 +313,7 @@ struct nl_model {
     unsigned int *d_ar_epoch = nullptr, *d_lg_epoch = nullptr;
     // one-pass prefill workspace (allocated on first use, sized for seq_len rows)
     float *pf_x = nullptr, *pf_qkv = nullptr, *pf_g = nullptr, *pf_u = nullptr; __nv_bfloat16 *pf_hi = nullptr, *pf_lo = nullptr; int pf_cap = 0;
+    float *pf_split = nullptr;   // split-K partial sums of the small-batch GEMMs (nl_gemm2.cuh), G2_SPLIT_BYTES
     bool pf_time = false; int pf_launches = 0;   // nl_bench_prefill: event after the token copy, kernels launched by the last prefill
     DevMat lm_view;   // this rank's vocab rows of the LM head (a view into output / tok_embd when tied; never freed)
     unsigned int *d_bar = nullptr; float *part_acc = nullptr, *part_ml = nullptr;   // grid-barrier counters, split-attention partials
@@ -673,7 +723,7 @@ static int ensure_pf(nl_model *m) {
     // sized once for the longest prompt and the largest batch: captured graphs keep these pointers
     const int rows = m->B > m->c.seq_len ? m->B : m->c.seq_len;
     if (m->pf_cap >= rows) return NL_OK;
-    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); m->pf_cap = 0; }
+    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); cudaFree(m->pf_split); m->pf_split = nullptr; m->pf_cap = 0; }
     const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, ld = qdim + 2 * kvd;
     const size_t T = (size_t)rows;
     size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
@@ -682,19 +732,21 @@ static int ensure_pf(nl_model *m) {
     NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
     NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
     NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
+    NL_CUDA(cudaMalloc(&m->pf_split, G2_SPLIT_BYTES));
     m->pf_cap = rows;
     return NL_OK;
 }
 
 #ifndef NL_BATCH_GEMM_MIN_DEFAULT
-#define NL_BATCH_GEMM_MIN_DEFAULT 0
+#define NL_BATCH_GEMM_MIN_DEFAULT 8
 #endif
-// Batched decode on the tensor cores (NL_BATCH_GEMM_MIN): B >= 16 sequences are B token
-// rows of the prefill GEMMs (tcgen05, weights dequantised once per 256 rows) instead of B accumulators of the CUDA-core GEMV, with the
-// per-sequence decode attention in between.  Every kernel on this path already runs in nl_prefill / the batch path.
+// Batched decode on the tensor cores (NL_BATCH_GEMM_MIN, default 8): B sequences are B token rows of the tcgen05
+// GEMMs in their tall orientation (nl_gemm2.cuh: the weights are the M side, the batch the N side, split K on the narrow matrices; the
+// weights are read once per step) instead of B accumulators of the CUDA-core GEMV (re-read once per 4 sequences), with the
+// per-sequence decode attention in between.  Measured on goldie Q4_0: B = 8 a tie (2.13 ms per step either way), B = 64 2.45 ms
+// against 14.35 ms.
 static bool batch_gemm_ok(const nl_model *m, int batch) {
-    // NL_BATCH_GEMM_MIN = smallest batch that takes this route (0 = never; the GEMM tiles are 128 rows tall, so a small batch wastes most
-    // of every MMA but still reads the weights once per step instead of once per 4 sequences)
+    // NL_BATCH_GEMM_MIN = smallest batch that takes this route (0 = never)
     const int bmin = getenv("NL_BATCH_GEMM_MIN") ? atoi(getenv("NL_BATCH_GEMM_MIN")) : (getenv("NL_BATCH_GEMM") ? 16 : NL_BATCH_GEMM_MIN_DEFAULT);
     if (bmin <= 0 || batch < bmin || batch < 2 || m->tp > 1) return false;
     const DevMat &out = m->output.present() ? m->output : m->tok_embd;
@@ -717,9 +769,10 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
         rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
-        if ((rc = gemm_run(ly.wq, m->pf_hi, m->pf_lo, B, ly.bq, m->q, qdim, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wk, m->pf_hi, m->pf_lo, B, ly.bk, m->k, kvd, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wv, m->pf_hi, m->pf_lo, B, ly.bv, m->v, kvd, GEPI_STORE, st))) return rc;
+        {
+            const GemmOut o[3] = {{&ly.wq, ly.bq, m->q, qdim, GEPI_STORE}, {&ly.wk, ly.bk, m->k, kvd, GEPI_STORE}, {&ly.wv, ly.bv, m->v, kvd, GEPI_STORE}};
+            if ((rc = gemm_run_multi(o, 3, m->pf_hi, m->pf_lo, B, st, nullptr, m->pf_split))) return rc;
+        }
         {   // RoPE, QK-norm, KV write, attention per sequence: model.go:530-587
             AttnArgs a;
             a.q = m->q; a.k = m->k; a.v = m->v;
@@ -733,21 +786,23 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
             else attn_decode_kernel<128><<<grid, 128, S * sizeof(float), st>>>(a);
         }
         if ((rc = split_planes(m->xb2, m->pf_hi, m->pf_lo, (int64_t)B * qdim, st))) return rc;
-        if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, B, ly.bo, m->x, dim, GEPI_RESID, st))) return rc;
+        if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, B, ly.bo, m->x, dim, GEPI_RESID, st, m->pf_split))) return rc;
         rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
-        if ((rc = gemm_run(ly.wgate, m->pf_hi, m->pf_lo, B, nullptr, m->pf_g, ffn, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wup, m->pf_hi, m->pf_lo, B, nullptr, m->pf_u, ffn, GEPI_STORE, st))) return rc;
+        {
+            const GemmOut o[2] = {{&ly.wgate, nullptr, m->pf_g, ffn, GEPI_STORE}, {&ly.wup, nullptr, m->pf_u, ffn, GEPI_STORE}};
+            if ((rc = gemm_run_multi(o, 2, m->pf_hi, m->pf_lo, B, st, nullptr, m->pf_split))) return rc;
+        }
         {
             const int64_t ne = (int64_t)B * ffn;
             swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
         }
-        if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, B, nullptr, m->x, dim, GEPI_RESID, st))) return rc;
+        if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, B, nullptr, m->x, dim, GEPI_RESID, st, m->pf_split))) return rc;
         launches += 12;
     }
     {   // final norm + LM head for every sequence, model.go:616-619
         const DevMat &out = m->output.present() ? m->output : m->tok_embd;
         rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, m->output_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
-        if ((rc = gemm_run(out, m->pf_hi, m->pf_lo, B, nullptr, m->logits, c.vocab_size, GEPI_STORE, st))) return rc;
+        if ((rc = gemm_run(out, m->pf_hi, m->pf_lo, B, nullptr, m->logits, c.vocab_size, GEPI_STORE, st, m->pf_split))) return rc;
         launches += 2;
     }
     NL_CUDA(cudaGetLastError());
@@ -1099,7 +1154,7 @@ void nl_destroy(nl_model *m) {
     }
     if (m->d_trace) cudaFree(m->d_trace);
     if (m->d_trace2) cudaFree(m->d_trace2);
-    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); }
+    if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); cudaFree(m->pf_split); }
     for (uint8_t *t : m->tile_bufs) if (t) cudaFree(t);
     for (void *q : {(void *)m->x_sh, (void *)m->qkv_sh, (void *)m->ao_sh, (void *)m->hb_sh, (void *)m->d_epoch, (void *)m->amax, (void *)m->arena}) if (q) cudaFree(q);
     if (m->qkv_bias) cudaFree(m->qkv_bias);
@@ -1236,14 +1291,15 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
         dim3 grid((dim + 255) / 256, n);
         embed_kernel<<<grid, 256, 0, st>>>(m->tok_embd, m->d_prompt, m->gamma, m->gamma_map, m->pf_x, dim);
     }
-    m->pf_launches = 1 + c.n_layers * 12 + 1;   // embedding; per layer 2 norms, 7 GEMMs, RoPE/KV write, attention, SwiGLU split; LM-head GEMV
+    m->pf_launches = 1 + c.n_layers * 7 + 1;   // embedding; per layer 2 norms, o and down GEMMs, RoPE/KV write, attention, SwiGLU split (q|k|v and gate|up: counted where they are launched); LM-head GEMV
     int rc;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
         rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
-        if ((rc = gemm_run(ly.wq, m->pf_hi, m->pf_lo, n, ly.bq, m->pf_qkv, ld, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wk, m->pf_hi, m->pf_lo, n, ly.bk, m->pf_qkv + qdim, ld, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wv, m->pf_hi, m->pf_lo, n, ly.bv, m->pf_qkv + qdim + kvd, ld, GEPI_STORE, st))) return rc;
+        {
+            const GemmOut o[3] = {{&ly.wq, ly.bq, m->pf_qkv, ld, GEPI_STORE}, {&ly.wk, ly.bk, m->pf_qkv + qdim, ld, GEPI_STORE}, {&ly.wv, ly.bv, m->pf_qkv + qdim + kvd, ld, GEPI_STORE}};
+            if ((rc = gemm_run_multi(o, 3, m->pf_hi, m->pf_lo, n, st, &m->pf_launches, m->pf_split))) return rc;
+        }
         PrefillAttn a;
         a.qkv = m->pf_qkv; a.ld = ld; a.T = n; a.pos0 = pos0;
         a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
@@ -1254,24 +1310,26 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
         if (getenv("NL_PREFILL_ATTN_CC")) attn_prefill_kernel<<<dim3(m->nH, (n + 31) / 32), 256, 0, st>>>(a);   // (A/B: the CUDA-core kernel)
         else attn_prefill_tc_kernel<<<dim3(m->nH, (n + PA_QT - 1) / PA_QT), 256, 0, st>>>(a);
         if (tpar) {   // row-split o-projection: this rank's partial, then the reduce-scatter / all-gather of the rows (nl_tp.cuh)
-            if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, pf_part, dim, GEPI_STORE, st))) return rc;
+            if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, pf_part, dim, GEPI_STORE, st, m->pf_split))) return rc;
             tp_reduce_rows_kernel<<<m->opts.num_sms, 256, 0, st>>>(n, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
             tp_rows_done_kernel<<<1, 32, 0, st>>>(m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
             m->pf_launches += 2;
-        } else if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st))) return rc;
+        } else if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st, m->pf_split))) return rc;
         rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
-        if ((rc = gemm_run(ly.wgate, m->pf_hi, m->pf_lo, n, nullptr, m->pf_g, ffn, GEPI_STORE, st))) return rc;
-        if ((rc = gemm_run(ly.wup, m->pf_hi, m->pf_lo, n, nullptr, m->pf_u, ffn, GEPI_STORE, st))) return rc;
+        {
+            const GemmOut o[2] = {{&ly.wgate, nullptr, m->pf_g, ffn, GEPI_STORE}, {&ly.wup, nullptr, m->pf_u, ffn, GEPI_STORE}};
+            if ((rc = gemm_run_multi(o, 2, m->pf_hi, m->pf_lo, n, st, &m->pf_launches, m->pf_split))) return rc;
+        }
         {
             const int64_t ne = (int64_t)n * ffn;
             swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
         }
         if (tpar) {
-            if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, pf_part, dim, GEPI_STORE, st))) return rc;
+            if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, pf_part, dim, GEPI_STORE, st, m->pf_split))) return rc;
             tp_reduce_rows_kernel<<<m->opts.num_sms, 256, 0, st>>>(n, dim, m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
             tp_rows_done_kernel<<<1, 32, 0, st>>>(m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
             m->pf_launches += 2;
-        } else if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, m->pf_x, dim, GEPI_RESID, st))) return rc;
+        } else if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, m->pf_x, dim, GEPI_RESID, st, m->pf_split))) return rc;
     }
     // the reference computes the LM head at every prompt position and uses only the last (go/main.go:160-166): last row only
     NL_CUDA(cudaMemcpyAsync(m->x, m->pf_x + (size_t)(n - 1) * dim, (size_t)dim * 4, cudaMemcpyDeviceToDevice, st));
@@ -1382,12 +1440,14 @@ int nl_bench_decode(nl_model *m, int32_t token, int32_t pos0, int32_t n_steps, f
         size_t n = (size_t)tg * tp_ * 8;
         std::vector<unsigned long long> h(n);
         NL_CUDA(cudaMemcpy(h.data(), m->d_trace, n * 8, cudaMemcpyDeviceToHost));
-        FILE *f = fopen(getenv("NL_TRACE"), "wb");
+        // tensor parallel: one file per rank (<NL_TRACE>.r<rank>)
+        const std::string p1 = std::string(getenv("NL_TRACE")) + (m->tp > 1 ? ".r" + std::to_string(m->rank) : std::string());
+        FILE *f = fopen(p1.c_str(), "wb");
         if (f) { int hdr[2] = {tg, tp_}; fwrite(hdr, 4, 2, f); fwrite(h.data(), 8, n, f); fclose(f); }
         if (m->d_trace2 && m->tile_ok) {   // clock64 sub-stamps -> <NL_TRACE>.ck
             std::vector<unsigned long long> h2(n * 2);
             NL_CUDA(cudaMemcpy(h2.data(), m->d_trace2, n * 16, cudaMemcpyDeviceToHost));
-            std::string p2 = std::string(getenv("NL_TRACE")) + ".ck";
+            std::string p2 = p1 + ".ck";
             FILE *f2 = fopen(p2.c_str(), "wb");
             if (f2) { int hdr2[2] = {tg, tp_}; fwrite(hdr2, 4, 2, f2); fwrite(h2.data(), 8, n * 2, f2); fclose(f2); }
         }
@@ -1436,6 +1496,7 @@ struct nl_matrix {
     std::vector<DevMat> copies;  // replicas for L2-cold benchmarking; [0] is the matrix
     float *x = nullptr, *out = nullptr; int xcap = 0;
     __nv_bfloat16 *xh = nullptr, *xl = nullptr;   // bf16 planes of x for the tensor-core path
+    float *split = nullptr;                       // split-K partial sums (nl_gemm2.cuh)
     cudaStream_t st = nullptr;
     GemvOpts opts{148, true, true};
     // batch-1 Q4_0: fragment-tiled replicas + one-phase descriptors for the tensor-core GEMV (nl_tile.cuh)
@@ -1495,6 +1556,7 @@ static int matrix_buffers(nl_matrix *w, int batch) {
     w->tph_cap = 0;   // the one-phase descriptors point at x / out
     NL_CUDA(cudaMalloc(&w->xh, (size_t)batch * w->copies[0].cols * 2));
     NL_CUDA(cudaMalloc(&w->xl, (size_t)batch * w->copies[0].cols * 2));
+    if (!w->split) NL_CUDA(cudaMalloc(&w->split, G2_SPLIT_BYTES));
     NL_CUDA(cudaMalloc(&w->x, (size_t)batch * w->copies[0].cols * 4));
     NL_CUDA(cudaMalloc(&w->out, (size_t)batch * w->copies[0].rows * 4));
     w->xcap = batch;
@@ -1510,7 +1572,7 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
     const int gemm_min = getenv("NL_GEMM_MIN_BATCH") ? atoi(getenv("NL_GEMM_MIN_BATCH")) : 16;
     if (batch >= gemm_min && gemm_eligible(m)) {   // many rows of x: the T-token GEMM on the tensor cores
         rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * m.cols, w->st); if (rc) return rc;
-        rc = gemm_run(m, w->xh, w->xl, batch, nullptr, w->out, (int)m.rows, GEPI_STORE, w->st); if (rc) return rc;
+        rc = gemm_run(m, w->xh, w->xl, batch, nullptr, w->out, (int)m.rows, GEPI_STORE, w->st, w->split); if (rc) return rc;
     } else if (batch == 1 && (rc = matrix_tiles(w, 1)) <= 0) {   // batch 1, Q4_0: the tensor-core GEMV of the decode path
         if (rc) return rc;
         rc = matrix_tiled_gemv(w, 0); if (rc) return rc;
@@ -1547,7 +1609,7 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     int idx = 0;
     for (int i = 0; i < warmup + iters; i++) {
         if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));
-        if (gemm) { rc = gemm_run(w->copies[idx], w->xh, w->xl, batch, nullptr, w->out, (int)src.rows, GEPI_STORE, w->st); if (rc) return rc; }
+        if (gemm) { rc = gemm_run(w->copies[idx], w->xh, w->xl, batch, nullptr, w->out, (int)src.rows, GEPI_STORE, w->st, w->split); if (rc) return rc; }
         else if (tiled == 0) { rc = matrix_tiled_gemv(w, idx); if (rc) return rc; }
         else {
             MatRef r = {&w->copies[idx], nullptr, nullptr, w->out, (int)src.rows};
@@ -1573,6 +1635,7 @@ void nl_matrix_destroy(nl_matrix *w) {
     if (w->d_tbar) cudaFree(w->d_tbar);
     if (w->x) cudaFree(w->x); if (w->out) cudaFree(w->out);
     if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
+    if (w->split) cudaFree(w->split);
     if (w->st) cudaStreamDestroy(w->st);
     delete w;
 }

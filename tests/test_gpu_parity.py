@@ -385,6 +385,30 @@ def test_batch_forward_matches_single(golden_dir, gold):
     m1.close(); mb.close()
 
 
+@pytest.mark.parametrize("name", ["tiny_gqa_q4_0", "tiny_gqa_q8_0", "tiny_gqa_f16"])
+def test_batch_forward_through_gemms_matches_single(golden_dir, gold, monkeypatch, name):
+    """NL_BATCH_GEMM_MIN: a decode batch as token rows of the tcgen05 GEMMs (tall orientation, split K, q|k|v and gate|up in one launch
+    each).  Same logits as the single-sequence path within the GEMM tolerance (bf16 hi/lo planes, three products)."""
+    monkeypatch.setenv("NL_BATCH_GEMM_MIN", "2")
+    gf = G.load_gguf(os.path.join(golden_dir, name + ".gguf"))
+    m1 = M.load_llama_model(gf)
+    B = 5
+    mb = M.load_llama_model(gf, max_batch=B)
+    toks = gold["tokens"]
+    seqs = [toks[i:i + 10] for i in range(B)]
+    singles = []
+    for s in seqs:
+        m1.reset()
+        for pos, t in enumerate(s):
+            m1.forward(int(t), pos)
+        singles.append(m1.state.logits.copy())
+    for pos in range(10):
+        out = mb.forward_batch([int(s[pos]) for s in seqs], [pos] * B)
+    for b in range(B):
+        assert maxrel(out[b], singles[b]) < 1e-4
+    m1.close(); mb.close()
+
+
 def test_gamma_injection(golden_dir, gold):
     gf = G.load_gguf(os.path.join(golden_dir, "tiny_gqa_q8_0.gguf"))
     m = M.load_llama_model(gf)
