@@ -221,6 +221,25 @@ def run_prefill(args, torch, dist, rank, world, local_rank):
         if dist:
             dist.barrier(); torch.cuda.synchronize()
 
+    # parity before timing, on every rank: the one-pass prefill of a 96-token prefix (tcgen05 GEMMs + tensor-core attention; under tensor
+    # parallelism the row exchanges) against the same tokens fed one Forward at a time like go/main.go:160-166 (the persistent decode
+    # kernel, which tests/ and the decode line check against the oracle at full depth)
+    parity = None
+    if not args.no_parity:
+        k = min(96, Tn)
+        m.reset(); m.prefill(toks[:k]); lp = m.state.logits.copy()
+        m.reset()
+        for i in range(k):
+            m.forward(int(toks[i]), i)
+        ls = m.state.logits.copy()
+        rel = float(np.abs(lp - ls).max() / max(float(np.abs(ls).max()), 1e-30))
+        worst = rel
+        if dist:
+            t = torch.tensor([rel], device="cuda"); dist.all_reduce(t, op=dist.ReduceOp.MAX); worst = float(t[0].item())
+        parity = {"prefix_tokens": k, "last_position_logits_maxrel_vs_token_by_token": worst, "argmax_identical": bool(int(lp.argmax()) == int(ls.argmax())),
+                  "tolerance": 1e-3, "ranks": world, "ok": bool(worst < 1e-3)}
+        if not parity["ok"]:
+            raise SystemExit(f"prefill parity check failed: {parity}")
     for _ in range(max(args.warmup, 1)):
         m.reset(); m.prefill(toks)
     sync_all()
@@ -259,7 +278,7 @@ def run_prefill(args, torch, dist, rank, world, local_rank):
                         "traffic": None, "peak_source": peaks["src"] + " bf16_tflops_sustained (kernels timed inside a long step)",
                         "useful_flops_per_step": flops, "how": "SURVEY 8d useful FLOPs (projections + causal attention + last-position LM head) / CUDA-event time"},
            "e2e": {"value": n_seq * Tn * len(e2e) / e2e_s, "unit": "tok/s", "h2d_bytes_per_step": 4 * Tn, "d2h_bytes_per_step": 4 * meta.vocab_size},
-           "gpu_launches": m.launches_last_prefill * args.steps}
+           "gpu_launches": m.launches_last_prefill * args.steps, "parity_check": parity}
     m.close()
     if rank == 0:
         print(json.dumps(out))

@@ -205,13 +205,14 @@ static int gemv_dispatch(const MatRef *mats, int nmat, const float *x, int x_str
 
 
 // C[T, rows] (=|+=) A[T, cols] · W^T on the tensor cores (nl_gemm.cuh).  a_hi / a_lo: bf16 planes of A, already split.
+static bool gemm_v1() { static const bool v = getenv("NL_GEMM_V1") != nullptr; return v; }
 static bool gemm_eligible(const DevMat &w) {
-    return (w.type == NL_Q4_0 || w.type == NL_Q8_0 || w.type == NL_F16) && w.cols % GM_BK == 0;
+    // K in whole quant blocks (the first-generation kernel steps by 64: an 8-way shard of big's down projection has 43 blocks per row)
+    return (w.type == NL_Q4_0 || w.type == NL_Q8_0 || w.type == NL_F16) && w.cols % (gemm_v1() ? GM_BK : G2_BK) == 0 && w.cols % 8 == 0;
 }
 // One launch for up to three matrices that share the input (q|k|v, gate|up): nl_gemm2.cuh.  NL_GEMM_V1=1 keeps the first-generation
-// kernel (one launch per matrix); F16 weights with more than 128 tokens stay with it too (no room for a raw ring next to 16 KB K steps).
+// kernel (one launch per matrix) for A/B runs.
 struct GemmOut { const DevMat *w; const float *bias; float *c; int ldc; int epi; };
-static bool gemm_v1() { static const bool v = getenv("NL_GEMM_V1") != nullptr; return v; }
 static int gemm_run1(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, const float *bias, float *c, int ldc, int epi, cudaStream_t st) {
     GemmArgs g; memset(&g, 0, sizeof g);
     g.a_hi = a_hi; g.a_lo = a_lo; g.qs = w.qs; g.d = w.d; g.bias = bias; g.c = c; g.T = T; g.N = (int)w.rows; g.K = (int)w.cols; g.ldc = ldc; g.epi = epi;
@@ -224,11 +225,10 @@ constexpr size_t G2_SPLIT_BYTES = 16u << 20;
 static int gemm_run_multi(const GemmOut *o, int n, const __nv_bfloat16 *a_hi, const __nv_bfloat16 *a_lo, int T, cudaStream_t st, int *launches = nullptr, float *split = nullptr) {
     bool same = n <= G2_MAX_SEG;
     for (int i = 1; i < n; i++) same = same && o[i].w->type == o[0].w->type && o[i].w->cols == o[0].w->cols;
-    const bool v1 = gemm_v1() || (o[0].w->type == NL_F16 && T > 128);
+    const bool v1 = gemm_v1();
     if (v1 || !same) {
         for (int i = 0; i < n; i++) {
-            int rc = (v1 || (o[i].w->type == NL_F16 && T > 128)) ? gemm_run1(*o[i].w, a_hi, a_lo, T, o[i].bias, o[i].c, o[i].ldc, o[i].epi, st)
-                                                                 : gemm_run_multi(&o[i], 1, a_hi, a_lo, T, st, nullptr, split);
+            int rc = v1 ? gemm_run1(*o[i].w, a_hi, a_lo, T, o[i].bias, o[i].c, o[i].ldc, o[i].epi, st) : gemm_run_multi(&o[i], 1, a_hi, a_lo, T, st, nullptr, split);
             if (rc) return rc;
             if (launches) (*launches)++;
         }
@@ -1577,7 +1577,7 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
         if (rc) return rc;
         rc = matrix_tiled_gemv(w, 0); if (rc) return rc;
     } else {
-        if (batch > 64) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 64 == 0", batch);
+        if (batch > 64) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 32 == 0", batch);
         MatRef r = {&m, nullptr, nullptr, w->out, (int)m.rows};
         rc = gemv_dispatch(&r, 1, w->x, (int)m.cols, batch, EPI_STORE, nullptr, 0.f, nullptr, w->opts, w->st, nullptr); if (rc) return rc;
     }
@@ -1592,7 +1592,7 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     int rc = matrix_buffers(w, batch); if (rc) return rc;
     const DevMat src = w->copies[0];
     const int gemm_min = getenv("NL_GEMM_MIN_BATCH") ? atoi(getenv("NL_GEMM_MIN_BATCH")) : 16;
-    if (batch > 64 && !(batch >= gemm_min && gemm_eligible(src))) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 64 == 0", batch);
+    if (batch > 64 && !(batch >= gemm_min && gemm_eligible(src))) return fail(NL_ERR_INVALID, "batch %d > 64 needs a Q4_0/Q8_0/F16 matrix with cols %% 32 == 0", batch);
     while ((int)w->copies.size() < n_copies) {
         DevMat c = src; c.qs = nullptr; c.d = nullptr;
         NL_CUDA(cudaMalloc(&c.qs, src.qs_bytes));

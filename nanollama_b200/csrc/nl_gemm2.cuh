@@ -428,6 +428,6 @@ int launch_gemm2_typed(const Gemm2Args &g, cudaStream_t st) {
 }
 int launch_gemm2_q4_0(const Gemm2Args &g, cudaStream_t st);
 int launch_gemm2_q8_0(const Gemm2Args &g, cudaStream_t st);
-int launch_gemm2_f16(const Gemm2Args &g, cudaStream_t st);   // tall only (T <= 128): the wide F16 shape stays with nl_gemm.cuh
+int launch_gemm2_f16(const Gemm2Args &g, cudaStream_t st);   // (wide: one 128-token tile per CTA)
 
 }  // namespace nl

@@ -629,9 +629,11 @@ def test_tensor_parallel_2gpu_parity():
 
 # ---------------------------------------------------------------- prefill: tcgen05 GEMM path
 @pytest.mark.parametrize("typ", [G.GGML_Q4_0, G.GGML_Q8_0, G.GGML_F16])
-@pytest.mark.parametrize("rows,cols,batch", [(128, 64, 16), (1000, 768, 200), (2048, 1536, 384)])
+@pytest.mark.parametrize("rows,cols,batch", [(128, 64, 16), (1000, 768, 200), (2048, 1536, 384), (520, 1376, 40), (300, 1376, 150), (4096, 4096, 64), (777, 1024, 129)])
 def test_matmul_many_rows_tensor_core_path(typ, rows, cols, batch):
-    """matmulDispatch with >= 16 activation rows runs as one tcgen05 GEMM (split-bf16, fp32 accumulate in TMEM)."""
+    """matmulDispatch with >= 16 activation rows runs as one tcgen05 GEMM (split-bf16, fp32 accumulate in TMEM): both orientations of
+    nl_gemm2.cuh (<= 128 rows: weights on the M side, narrow matrices split along K; above: one or two 128-row tiles per CTA), K with
+    an odd number of quant blocks (1376 = an 8-way shard of big's down projection), ragged N and T."""
     rng = np.random.default_rng(rows + cols + batch + typ)
     raw = G.encode_tensor((rng.standard_normal((rows, cols)) / np.sqrt(cols)).astype(np.float32), typ)
     x = rng.standard_normal((batch, cols)).astype(np.float32)

@@ -23,7 +23,7 @@ if __name__ == "__main__":
     for typ, name in ((G.GGML_Q4_0, "q4_0"), (G.GGML_Q8_0, "q8_0"), (G.GGML_F16, "f16")):
         # batch <= 128: the tall orientation (weights on the M side, split K when the matrix is narrow); above: the wide one
         for rows, cols, batch in ((128, 64, 128), (256, 256, 128), (1000, 768, 200), (4096, 1536, 512), (300, 128, 16), (1536, 4096, 17), (2304, 1536, 64),
-                                 (520, 2048, 100), (777, 1024, 129), (4096, 4096, 300)):
+                                 (520, 2048, 100), (777, 1024, 129), (4096, 4096, 300), (520, 1376, 40), (300, 1376, 150)):
             try:
                 print(name, rows, cols, batch, "max-rel", "%.3e" % run(typ, rows, cols, batch), flush=True)
             except Exception as e:
