@@ -206,6 +206,15 @@ static int gemv_dispatch(const MatRef *mats, int nmat, const float *x, int x_str
 
 // C[T, rows] (=|+=) A[T, cols] · W^T on the tensor cores (nl_gemm.cuh).  a_hi / a_lo: bf16 planes of A, already split.
 static bool gemm_v1() { static const bool v = getenv("NL_GEMM_V1") != nullptr; return v; }
+#ifndef NL_GEMM_ATILE_DEFAULT
+#define NL_GEMM_ATILE_DEFAULT 1
+#endif
+// NL_GEMM_ATILE: the producers of a GEMM input write its bf16 planes in tile order (plane_index, nl_common.cuh) and the GEMM's issuing
+// thread fetches every 128-row x 32-k tile with one bulk copy, instead of 256 threads issuing 16-byte cp.async for it
+static int gemm_atile() {
+    static const int v = gemm_v1() ? 0 : (getenv("NL_GEMM_ATILE") ? atoi(getenv("NL_GEMM_ATILE")) != 0 : NL_GEMM_ATILE_DEFAULT);
+    return v;
+}
 static bool gemm_eligible(const DevMat &w) {
     // K in whole quant blocks (the first-generation kernel steps by 64: an 8-way shard of big's down projection has 43 blocks per row)
     return (w.type == NL_Q4_0 || w.type == NL_Q8_0 || w.type == NL_F16) && w.cols % (gemm_v1() ? GM_BK : G2_BK) == 0 && w.cols % 8 == 0;
@@ -235,7 +244,7 @@ static int gemm_run_multi(const GemmOut *o, int n, const __nv_bfloat16 *a_hi, co
         return NL_OK;
     }
     Gemm2Args g; memset(&g, 0, sizeof g);
-    g.a_hi = a_hi; g.a_lo = a_lo; g.nseg = n; g.T = T; g.K = (int)o[0].w->cols;
+    g.a_hi = a_hi; g.a_lo = a_lo; g.nseg = n; g.T = T; g.K = (int)o[0].w->cols; g.a_tiled = gemm_atile();
     int tiles = 0;
     for (int i = 0; i < n; i++) {
         const DevMat &w = *o[i].w;
@@ -264,9 +273,9 @@ static int gemm_run(const DevMat &w, const __nv_bfloat16 *a_hi, const __nv_bfloa
     const GemmOut o{&w, bias, c, ldc, epi};
     return gemm_run_multi(&o, 1, a_hi, a_lo, T, st, nullptr, split);
 }
-static int split_planes(const float *x, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t n, cudaStream_t st) {
+static int split_planes(const float *x, __nv_bfloat16 *hi, __nv_bfloat16 *lo, int64_t n, int K, cudaStream_t st) {
     const int64_t pairs = (n + 1) / 2;
-    split_bf16_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(x, hi, lo, n);
+    split_bf16_kernel<<<(unsigned)((pairs + 255) / 256), 256, 0, st>>>(x, hi, lo, n, K, gemm_atile());
     NL_CUDA(cudaGetLastError());
     return NL_OK;
 }
@@ -726,12 +735,13 @@ static int ensure_pf(nl_model *m) {
     if (m->pf_cap) { if (m->tp == 1) cudaFree(m->pf_x); cudaFree(m->pf_qkv); cudaFree(m->pf_g); cudaFree(m->pf_u); cudaFree(m->pf_hi); cudaFree(m->pf_lo); cudaFree(m->pf_split); m->pf_split = nullptr; m->pf_cap = 0; }
     const int dim = m->dim, qdim = m->qdim, kvd = m->kvd, ffn = m->ffn, ld = qdim + 2 * kvd;
     const size_t T = (size_t)rows;
+    const size_t Tt = (T + 127) & ~(size_t)127;   // the bf16 planes in whole 128-row tiles (plane_index order reads whole tiles)
     size_t wide = dim > qdim ? dim : qdim; if ((size_t)ffn > wide) wide = ffn;
     if (m->tp > 1) m->pf_x = reinterpret_cast<float *>(m->tp_win + m->tp_lay.pf_x);   // tensor parallel: the residual rows live in the window (nl_tp.cuh)
     else NL_CUDA(cudaMalloc(&m->pf_x, T * dim * 4));
     NL_CUDA(cudaMalloc(&m->pf_qkv, T * ld * 4));
     NL_CUDA(cudaMalloc(&m->pf_g, T * ffn * 4)); NL_CUDA(cudaMalloc(&m->pf_u, T * ffn * 4));
-    NL_CUDA(cudaMalloc(&m->pf_hi, T * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, T * wide * 2));
+    NL_CUDA(cudaMalloc(&m->pf_hi, Tt * wide * 2)); NL_CUDA(cudaMalloc(&m->pf_lo, Tt * wide * 2));
     NL_CUDA(cudaMalloc(&m->pf_split, G2_SPLIT_BYTES));
     m->pf_cap = rows;
     return NL_OK;
@@ -768,7 +778,7 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
     }
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
-        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps, gemm_atile());
         {
             const GemmOut o[3] = {{&ly.wq, ly.bq, m->q, qdim, GEPI_STORE}, {&ly.wk, ly.bk, m->k, kvd, GEPI_STORE}, {&ly.wv, ly.bv, m->v, kvd, GEPI_STORE}};
             if ((rc = gemm_run_multi(o, 3, m->pf_hi, m->pf_lo, B, st, nullptr, m->pf_split))) return rc;
@@ -785,23 +795,23 @@ static int record_forward_batch_gemm(nl_model *m, int batch) {
             if (hd == 64) attn_decode_kernel<64><<<grid, 128, S * sizeof(float), st>>>(a);
             else attn_decode_kernel<128><<<grid, 128, S * sizeof(float), st>>>(a);
         }
-        if ((rc = split_planes(m->xb2, m->pf_hi, m->pf_lo, (int64_t)B * qdim, st))) return rc;
+        if ((rc = split_planes(m->xb2, m->pf_hi, m->pf_lo, (int64_t)B * qdim, qdim, st))) return rc;
         if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, B, ly.bo, m->x, dim, GEPI_RESID, st, m->pf_split))) return rc;
-        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps, gemm_atile());
         {
             const GemmOut o[2] = {{&ly.wgate, nullptr, m->pf_g, ffn, GEPI_STORE}, {&ly.wup, nullptr, m->pf_u, ffn, GEPI_STORE}};
             if ((rc = gemm_run_multi(o, 2, m->pf_hi, m->pf_lo, B, st, nullptr, m->pf_split))) return rc;
         }
         {
             const int64_t ne = (int64_t)B * ffn;
-            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
+            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne, ffn, gemm_atile());
         }
         if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, B, nullptr, m->x, dim, GEPI_RESID, st, m->pf_split))) return rc;
         launches += 12;
     }
     {   // final norm + LM head for every sequence, model.go:616-619
         const DevMat &out = m->output.present() ? m->output : m->tok_embd;
-        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, m->output_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        rmsnorm_split_kernel<<<B, 256, 0, st>>>(m->x, m->output_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps, gemm_atile());
         if ((rc = gemm_run(out, m->pf_hi, m->pf_lo, B, nullptr, m->logits, c.vocab_size, GEPI_STORE, st, m->pf_split))) return rc;
         launches += 2;
     }
@@ -1295,7 +1305,7 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
     int rc;
     for (int l = 0; l < c.n_layers; l++) {
         Layer &ly = m->L[l];
-        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.attn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps, gemm_atile());
         {
             const GemmOut o[3] = {{&ly.wq, ly.bq, m->pf_qkv, ld, GEPI_STORE}, {&ly.wk, ly.bk, m->pf_qkv + qdim, ld, GEPI_STORE}, {&ly.wv, ly.bv, m->pf_qkv + qdim + kvd, ld, GEPI_STORE}};
             if ((rc = gemm_run_multi(o, 3, m->pf_hi, m->pf_lo, n, st, &m->pf_launches, m->pf_split))) return rc;
@@ -1303,7 +1313,7 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
         PrefillAttn a;
         a.qkv = m->pf_qkv; a.ld = ld; a.T = n; a.pos0 = pos0;
         a.kcache = m->kc + (int64_t)l * S * kvd; a.vcache = m->vc + (int64_t)l * S * kvd;
-        a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.out_hi = m->pf_hi; a.out_lo = m->pf_lo;
+        a.cos_t = m->cos_t; a.sin_t = m->sin_t; a.out_hi = m->pf_hi; a.out_lo = m->pf_lo; a.tiled = gemm_atile();
         a.n_heads = m->nH; a.n_kv_heads = m->nKV; a.qk_norm = c.qk_norm; a.conj = c.rope_conjugate; a.eps = c.rms_norm_eps;
         a.scale = (float)(1.0 / sqrt((double)m->hd));
         rope_kv_kernel<<<n, 256, 0, st>>>(a);
@@ -1315,14 +1325,14 @@ static int prefill_gemm(nl_model *m, const int32_t *tokens, int n, int pos0) {
             tp_rows_done_kernel<<<1, 32, 0, st>>>(m->tp_peers, m->tp_lay, m->rank, m->tp, m->d_pf_epoch);
             m->pf_launches += 2;
         } else if ((rc = gemm_run(ly.wo, m->pf_hi, m->pf_lo, n, ly.bo, m->pf_x, dim, GEPI_RESID, st, m->pf_split))) return rc;
-        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps);
+        rmsnorm_split_kernel<<<n, 256, 0, st>>>(m->pf_x, ly.ffn_norm, m->pf_hi, m->pf_lo, dim, c.rms_norm_eps, gemm_atile());
         {
             const GemmOut o[2] = {{&ly.wgate, nullptr, m->pf_g, ffn, GEPI_STORE}, {&ly.wup, nullptr, m->pf_u, ffn, GEPI_STORE}};
             if ((rc = gemm_run_multi(o, 2, m->pf_hi, m->pf_lo, n, st, &m->pf_launches, m->pf_split))) return rc;
         }
         {
             const int64_t ne = (int64_t)n * ffn;
-            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne);
+            swiglu_split_kernel<<<(unsigned)((ne / 2 + 255) / 256), 256, 0, st>>>(m->pf_g, m->pf_u, m->pf_hi, m->pf_lo, ne, ffn, gemm_atile());
         }
         if (tpar) {
             if ((rc = gemm_run(ly.wdown, m->pf_hi, m->pf_lo, n, nullptr, pf_part, dim, GEPI_STORE, st, m->pf_split))) return rc;
@@ -1554,8 +1564,9 @@ static int matrix_buffers(nl_matrix *w, int batch) {
     if (w->xh) cudaFree(w->xh); if (w->xl) cudaFree(w->xl);
     w->x = w->out = nullptr; w->xh = w->xl = nullptr;
     w->tph_cap = 0;   // the one-phase descriptors point at x / out
-    NL_CUDA(cudaMalloc(&w->xh, (size_t)batch * w->copies[0].cols * 2));
-    NL_CUDA(cudaMalloc(&w->xl, (size_t)batch * w->copies[0].cols * 2));
+    const size_t bt = ((size_t)batch + 127) & ~(size_t)127;   // (whole 128-row tiles, see ensure_pf)
+    NL_CUDA(cudaMalloc(&w->xh, bt * w->copies[0].cols * 2));
+    NL_CUDA(cudaMalloc(&w->xl, bt * w->copies[0].cols * 2));
     if (!w->split) NL_CUDA(cudaMalloc(&w->split, G2_SPLIT_BYTES));
     NL_CUDA(cudaMalloc(&w->x, (size_t)batch * w->copies[0].cols * 4));
     NL_CUDA(cudaMalloc(&w->out, (size_t)batch * w->copies[0].rows * 4));
@@ -1571,7 +1582,7 @@ int nl_matrix_matmul(nl_matrix *w, const float *host_x, int32_t batch, float *ho
     NL_CUDA(cudaMemcpyAsync(w->x, host_x, (size_t)batch * m.cols * 4, cudaMemcpyHostToDevice, w->st));
     const int gemm_min = getenv("NL_GEMM_MIN_BATCH") ? atoi(getenv("NL_GEMM_MIN_BATCH")) : 16;
     if (batch >= gemm_min && gemm_eligible(m)) {   // many rows of x: the T-token GEMM on the tensor cores
-        rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * m.cols, w->st); if (rc) return rc;
+        rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * m.cols, (int)m.cols, w->st); if (rc) return rc;
         rc = gemm_run(m, w->xh, w->xl, batch, nullptr, w->out, (int)m.rows, GEPI_STORE, w->st, w->split); if (rc) return rc;
     } else if (batch == 1 && (rc = matrix_tiles(w, 1)) <= 0) {   // batch 1, Q4_0: the tensor-core GEMV of the decode path
         if (rc) return rc;
@@ -1605,7 +1616,7 @@ int nl_matrix_bench(nl_matrix *w, int32_t batch, int32_t n_copies, int32_t warmu
     const int tiled = batch == 1 ? matrix_tiles(w, n_copies) : 1;
     if (tiled < 0) return tiled;
     const bool gemm = batch >= gemm_min && gemm_eligible(src);   // the T-row GEMM on the tensor cores (the activation planes are split once, outside the timed loop)
-    if (gemm) { rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * src.cols, w->st); if (rc) return rc; }
+    if (gemm) { rc = split_planes(w->x, w->xh, w->xl, (int64_t)batch * src.cols, (int)src.cols, w->st); if (rc) return rc; }
     int idx = 0;
     for (int i = 0; i < warmup + iters; i++) {
         if (i == warmup) NL_CUDA(cudaEventRecord(e0, w->st));

@@ -46,6 +46,14 @@ struct DevMat {
     size_t bytes() const { return qs_bytes + d_bytes; }
 };
 
+// Element index of activation (row, k) inside one bf16 plane of a GEMM input: row-major [T][K], or (tiled != 0) the order in which
+// nl_gemm2.cuh wants it in shared memory, so that a 128-row x 32-k tile is ONE contiguous 8 KB piece a bulk copy can fetch:
+// tiles [row / 128][k / 32], inside a tile the K-major UMMA core-matrix order [k / 8 % 4][row % 128 / 8][row % 8][k % 8].
+__host__ __device__ __forceinline__ size_t plane_index(int row, int k, int K, int tiled) {
+    if (!tiled) return (size_t)row * K + k;
+    return ((size_t)(row >> 7) * (size_t)(K >> 5) + (size_t)(k >> 5)) * 4096 + (size_t)(((k >> 3) & 3) * 1024 + ((row & 127) >> 3) * 64 + (row & 7) * 8 + (k & 7));
+}
+
 // ---- small device helpers ----
 __device__ __forceinline__ float warp_sum(float v) {
 #pragma unroll

@@ -256,13 +256,14 @@ __global__ void __launch_bounds__(GM_THREADS, 1) gemm_tc_kernel(const GemmArgs g
 }
 
 // fp32 [n] -> bf16 hi / lo planes (exact two-term split up to 16 bits)
-static __global__ void split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t n) {
+static __global__ void split_bf16_kernel(const float *__restrict__ x, __nv_bfloat16 *__restrict__ hi, __nv_bfloat16 *__restrict__ lo, int64_t n, int K, int tiled) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i + 1 < n) {
         uint32_t h, l;
         split2(x[i], x[i + 1], h, l);
-        *reinterpret_cast<uint32_t *>(hi + i) = h;
-        *reinterpret_cast<uint32_t *>(lo + i) = l;
+        const size_t o = tiled ? plane_index((int)(i / K), (int)(i % K), K, 1) : (size_t)i;   // (tiled: K is a multiple of 32)
+        *reinterpret_cast<uint32_t *>(hi + o) = h;
+        *reinterpret_cast<uint32_t *>(lo + o) = l;
     } else if (i < n) {
         const __nv_bfloat16 hx = __float2bfloat16_rn(x[i]);
         hi[i] = hx; lo[i] = __float2bfloat16_rn(x[i] - __bfloat162float(hx));

@@ -48,6 +48,7 @@ struct Gemm2Args {
     const __nv_bfloat16 *a_hi, *a_lo;   // [T][K] row-major
     Gemm2Seg seg[G2_MAX_SEG];
     int nseg, T, K;
+    int a_tiled;   // the planes are in plane_index order (nl_common.cuh): the issuing warp fetches every 8 KB tile with ONE bulk copy
     // split K (tall only): grid.z CTAs share one tile, each takes `ksplit_steps` K steps and leaves its partial sums in
     // part[z][T][ldp] (column = 256 * tile + column in tile); gemm2_reduce_kernel adds them in z order and applies bias / residual
     int ksplit, ksplit_steps, ldp;
@@ -109,6 +110,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const Gemm2Args g)
     static_assert(RD >= 2, "the raw ring has to run at least two K steps ahead (cp.async group accounting)");
     extern __shared__ __align__(1024) uint8_t smem[];
     __shared__ uint64_t mma_bar[2];
+    __shared__ uint64_t a_full[G2_A_SLOTS];   // (tiled planes) the bulk copies of a step's activation tiles have landed
     __shared__ uint32_t tmem_base_s;
     const int tid = threadIdx.x, warp = tid >> 5, lane = tid & 31;
 
@@ -125,6 +127,7 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const Gemm2Args g)
 
     if (tid == 0) {
         mbar_init(&mma_bar[0], 1); mbar_init(&mma_bar[1], 1);
+        for (int i = 0; i < G2_A_SLOTS; i++) mbar_init(&a_full[i], 1);
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
     if (warp == 0) {
@@ -142,9 +145,30 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const Gemm2Args g)
         const uint32_t idesc = WIDE ? ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(G2_BN >> 3) << 17) | ((uint32_t)(128 >> 4) << 24))
                                     : ((1u << 4) | (1u << 7) | (1u << 10) | ((uint32_t)(Tp >> 3) << 17) | ((uint32_t)(128 >> 4) << 24));
         const uint32_t a0 = g2_desc_lo(sm + Cfg::A_OFF, G2_A_LBO), w0 = g2_desc_lo(sm + Cfg::W_OFF, G2_W_LBO);
+        // tiled planes: this thread also fetches the activation tiles, two steps ahead, one bulk copy per (128-row tile, plane); a tile
+        // whose rows are all beyond T is skipped (the planes are allocated in whole tiles up to T)
+        int n_mt = 0;
+        for (int mt = 0; mt < MT; mt++) n_mt += (m0 + mt * 128 < g.T) ? 1 : 0;
+        auto fetch_a = [&](int ks) {
+            uint64_t *bar = &a_full[ks & (G2_A_SLOTS - 1)];
+            uint8_t *slot = smem + Cfg::A_OFF + (size_t)(ks & (G2_A_SLOTS - 1)) * Cfg::A_SLOT;
+            mbar_expect_tx(bar, (uint32_t)(n_mt * 2 * G2_A_TILE));
+            for (int mt = 0; mt < n_mt; mt++) {
+                const size_t e = ((size_t)((m0 >> 7) + mt) * (size_t)nb + (size_t)(ks0 + ks)) * (G2_A_TILE / 2);
+                bulk_g2s(slot + (size_t)mt * (2 * G2_A_TILE), g.a_hi + e, G2_A_TILE, bar);
+                bulk_g2s(slot + (size_t)mt * (2 * G2_A_TILE) + G2_A_TILE, g.a_lo + e, G2_A_TILE, bar);
+            }
+        };
+        if (g.a_tiled && lane == 0) { fetch_a(0); if (ksteps > 1) fetch_a(1); }
         for (int ks = 0; ks < ksteps; ks++) {
             if (ks & 1) g2_bar_sync<2>(); else g2_bar_sync<1>();   // every producer's part of step ks is in shared memory (and fenced)
             if (lane == 0) {
+                if (g.a_tiled) {
+                    // (every producer has seen the commit of step ks - 2 before it arrived for step ks: this wait does not block, and it
+                    // sits in front of this step's commit so that the barrier cannot be two phases ahead of the parity asked for)
+                    if (ks + 2 < ksteps) { if (ks >= 2) mbar_wait(&mma_bar[ks & 1], ((ks >> 1) - 1) & 1); fetch_a(ks + 2); }
+                    mbar_wait(&a_full[ks & (G2_A_SLOTS - 1)], (ks >> 2) & 1);
+                }
                 asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory");
                 const uint32_t al = a0 + (uint32_t)((ks & (G2_A_SLOTS - 1)) * (Cfg::A_SLOT >> 4));   // (descriptor words count 16-byte units)
                 const uint32_t wl = w0 + (uint32_t)((ks & 1) * (Cfg::W_SLOT >> 4));
@@ -218,14 +242,14 @@ __global__ void __launch_bounds__(G2_THREADS, 1) gemm2_kernel(const Gemm2Args g)
     // ---- prologue: the raw ring RD steps deep, the A ring two steps deep; one cp.async group per (virtual) iteration
     for (int v = -RD; v < 0; v++) {
         if (v + RD < ksteps) issue_raw(v + RD);
-        if (v + 2 >= 0 && v + 2 < ksteps) issue_a(v + 2);
+        if (!g.a_tiled && v + 2 >= 0 && v + 2 < ksteps) issue_a(v + 2);
         asm volatile("cp.async.commit_group;" ::: "memory");
     }
 
     for (int ks = 0; ks < ksteps; ks++) {
         // stage reuse: the MMAs of step ks - 2 read W slot ks & 1 and A slot (ks + 2) & 3
         if (ks >= 2) mbar_wait(&mma_bar[ks & 1], ((ks >> 1) - 1) & 1);
-        if (ks + 2 < ksteps) issue_a(ks + 2);
+        if (!g.a_tiled && ks + 2 < ksteps) issue_a(ks + 2);
         // (the raw slot of step ks + RD is the one step ks - 1 was read from: RS = RD + 1 slots)
         if (ks + RD < ksteps) issue_raw(ks + RD);
         asm volatile("cp.async.commit_group;" ::: "memory");

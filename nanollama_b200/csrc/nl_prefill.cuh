@@ -11,7 +11,7 @@ namespace nl {
 
 // out planes [T][n] = split_bf16(x[t] * inv_rms(x[t]) * w)      RMSNormInto, go/quant.go:597-607
 static __global__ void __launch_bounds__(256) rmsnorm_split_kernel(const float *__restrict__ x, const float *__restrict__ w, __nv_bfloat16 *__restrict__ hi,
-                                                                   __nv_bfloat16 *__restrict__ lo, int n, float eps) {
+                                                                   __nv_bfloat16 *__restrict__ lo, int n, float eps, int tiled) {
     const float *xi = x + (size_t)blockIdx.x * n;
     double ss = 0.0;
     for (int i = threadIdx.x; i < n; i += blockDim.x) { const double v = (double)xi[i]; ss += v * v; }
@@ -30,20 +30,22 @@ static __global__ void __launch_bounds__(256) rmsnorm_split_kernel(const float *
     for (int i = threadIdx.x * 2; i < n; i += blockDim.x * 2) {
         uint32_t h, l;
         split2(xi[i] * inv * w[i], xi[i + 1] * inv * w[i + 1], h, l);
-        *reinterpret_cast<uint32_t *>(hi + (size_t)blockIdx.x * n + i) = h;
-        *reinterpret_cast<uint32_t *>(lo + (size_t)blockIdx.x * n + i) = l;
+        const size_t o = plane_index((int)blockIdx.x, i, n, tiled);
+        *reinterpret_cast<uint32_t *>(hi + o) = h;
+        *reinterpret_cast<uint32_t *>(lo + o) = l;
     }
 }
 
 // planes = split_bf16(SiLU(gate) * up)                           go/model.go:604-606
 static __global__ void swiglu_split_kernel(const float *__restrict__ gate, const float *__restrict__ up, __nv_bfloat16 *__restrict__ hi,
-                                           __nv_bfloat16 *__restrict__ lo, int64_t n) {
+                                           __nv_bfloat16 *__restrict__ lo, int64_t n, int K, int tiled) {
     const int64_t i = ((int64_t)blockIdx.x * blockDim.x + threadIdx.x) * 2;
     if (i + 1 < n) {
         uint32_t h, l;
         split2(silu_f(gate[i]) * up[i], silu_f(gate[i + 1]) * up[i + 1], h, l);
-        *reinterpret_cast<uint32_t *>(hi + i) = h;
-        *reinterpret_cast<uint32_t *>(lo + i) = l;
+        const size_t o = tiled ? plane_index((int)(i / K), (int)(i % K), K, 1) : (size_t)i;   // (K is even: a pair never straddles two rows)
+        *reinterpret_cast<uint32_t *>(hi + o) = h;
+        *reinterpret_cast<uint32_t *>(lo + o) = l;
     }
 }
 
@@ -52,7 +54,8 @@ struct PrefillAttn {
     int ld, T, pos0;
     float *kcache, *vcache;      // this layer's slab [S][kvd]
     const float *cos_t, *sin_t;  // [S][32]
-    __nv_bfloat16 *out_hi, *out_lo;  // [T][qdim]
+    __nv_bfloat16 *out_hi, *out_lo;  // [T][qdim] (tiled: plane_index order)
+    int tiled;
     int n_heads, n_kv_heads, qk_norm, conj;
     float eps, scale;
 };
@@ -155,10 +158,10 @@ static __global__ void __launch_bounds__(256) attn_prefill_kernel(const PrefillA
         const float inv = 1.0f / l_run[j];
         const float o0 = acc0[j] * inv, o1 = acc1[j] * inv;
         const __nv_bfloat16 h0 = __float2bfloat16_rn(o0), h1 = __float2bfloat16_rn(o1);
-        const size_t base = (size_t)t * qdim + h * HD;
-        a.out_hi[base + lane] = h0; a.out_hi[base + lane + 32] = h1;
-        a.out_lo[base + lane] = __float2bfloat16_rn(o0 - __bfloat162float(h0));
-        a.out_lo[base + lane + 32] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
+        const size_t b0 = plane_index(t, h * HD + lane, qdim, a.tiled), b1 = plane_index(t, h * HD + lane + 32, qdim, a.tiled);
+        a.out_hi[b0] = h0; a.out_hi[b1] = h1;
+        a.out_lo[b0] = __float2bfloat16_rn(o0 - __bfloat162float(h0));
+        a.out_lo[b1] = __float2bfloat16_rn(o1 - __bfloat162float(h1));
     }
 }
 
@@ -289,11 +292,13 @@ static __global__ void __launch_bounds__(256) attn_prefill_tc_kernel(const Prefi
         uint32_t hh, ll;
         if (r0 < a.T) {
             split2(o[d][0] * i0, o[d][1] * i0, hh, ll);
-            *reinterpret_cast<uint32_t *>(a.out_hi + (size_t)r0 * qdim + col) = hh; *reinterpret_cast<uint32_t *>(a.out_lo + (size_t)r0 * qdim + col) = ll;
+            const size_t o0 = plane_index(r0, col, qdim, a.tiled);
+            *reinterpret_cast<uint32_t *>(a.out_hi + o0) = hh; *reinterpret_cast<uint32_t *>(a.out_lo + o0) = ll;
         }
         if (r1 < a.T) {
             split2(o[d][2] * i1, o[d][3] * i1, hh, ll);
-            *reinterpret_cast<uint32_t *>(a.out_hi + (size_t)r1 * qdim + col) = hh; *reinterpret_cast<uint32_t *>(a.out_lo + (size_t)r1 * qdim + col) = ll;
+            const size_t o1 = plane_index(r1, col, qdim, a.tiled);
+            *reinterpret_cast<uint32_t *>(a.out_hi + o1) = hh; *reinterpret_cast<uint32_t *>(a.out_lo + o1) = ll;
         }
     }
 }
