@@ -9,8 +9,12 @@
 //   * one CTA owns 256 output columns (tcgen05.mma M=128, N=256): half the A traffic per flop; four lanes fetch one row's 64 bytes, so
 //     every sector that crosses the L2 -> SM link is used whole;
 //   * K step 32 = one quant block per weight row: thread n dequantises row n's block, nothing else — 256 threads, 256 rows;
-//   * separate rings: A tiles four deep (cp.async issued two steps ahead), dequantised W two deep, raw quantised W in a shared-memory
-//     ring up to 15 steps deep (cp.async, 60 KB in flight per SM: what an HBM-bound small batch needs);
+//   * separate rings: A tiles four deep (fetched two steps ahead), dequantised W two deep, raw quantised W in a shared-memory ring up
+//     to 15 steps deep (cp.async, 60 KB in flight per SM: what an HBM-bound small batch needs);
+//   * the activation planes come in TILE ORDER (plane_index, nl_common.cuh: their producers write a 128-row x 32-k tile as one
+//     contiguous 8 KB piece, already in the UMMA core-matrix order) and the issuing thread fetches each tile with one cp.async.bulk
+//     that completes on an mbarrier.  (a_tiled = 0: row-major planes, 256 threads x 8 cp.async per step -- their address registers are
+//     held until the memory pipe takes each copy: 22 % of the producers' stall samples, 333 instead of 433 TFLOP/s at 2048 rows);
 //   * two orientations.  WIDE (T > 128): activations are the M side, two 128-token tiles share every dequantised W tile (TMEM: 2 x 256
 //     columns).  TALL (T <= 128): the WEIGHTS are the M side (two blocks of 128 rows) and the tokens are the N side, N = T rounded up
 //     to 16 — a 16-sequence decode batch costs 1/8 of the tensor-core time of a 128-token tile instead of all of it, and the epilogue
