@@ -6,8 +6,8 @@
 // in fp32 in TMEM); what changed is how the operands get to the tensor core.  The first kernel was bound by the way it fed itself: its
 // A tiles were re-read from L2 in 16-byte pieces of 32-byte sectors (2x the bytes) once per 128 output columns, and only one K step
 // of weights was in flight per SM.  Here:
-//   * one CTA owns 256 output columns (tcgen05.mma M=128, N=256): half the A traffic per flop; four lanes fetch one row's 64 bytes, so
-//     every sector that crosses the L2 -> SM link is used whole;
+//   * one CTA owns 256 output columns (tcgen05.mma M=128, N=256): half the A traffic per flop, and every sector that crosses the
+//     L2 -> SM link is used whole (tile-order planes: 8 KB pieces; row-major planes: four lanes fetch one row's 64 bytes);
 //   * K step 32 = one quant block per weight row: thread n dequantises row n's block, nothing else — 256 threads, 256 rows;
 //   * separate rings: A tiles four deep (fetched two steps ahead), dequantised W two deep, raw quantised W in a shared-memory ring up
 //     to 15 steps deep (cp.async, 60 KB in flight per SM: what an HBM-bound small batch needs);
